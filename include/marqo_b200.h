@@ -1,0 +1,199 @@
+/* marqo_b200 — C ABI of the B200-native embed-and-score engine.
+ *
+ * The reference (marqo-ai/marqo) has NO foreign-function interface on this path: it calls
+ * open_clip / transformers / torch for the encoders and an HTTP POST to Vespa for the score
+ * step.  This header is therefore the boundary a Marqo maintainer would bind from Python
+ * (ctypes — see INTEGRATION.md) underneath the reference's two pure-Python seams:
+ *
+ *   B1  encoder seam   model.encode(...) objects held by s2_inference._available_models
+ *                      (src/marqo/s2_inference/s2_inference.py:123-158, :520-568;
+ *                       loaders map src/marqo/s2_inference/model_registry.py:2133-2145)
+ *   B2  score seam     VespaClient.query()/feed_batch()
+ *                      (src/marqo/vespa/vespa_client.py:198-242, :267-296), consumed at
+ *                      src/marqo/tensor_search/tensor_search.py:2189 and
+ *                      src/marqo/core/vespa_index/add_documents_handler.py:177
+ *
+ * Conventions: plain C, opaque handles, caller-owned host buffers, every function returns an
+ * int status (B200_OK == 0) and leaves a thread-local message readable through
+ * b200_last_error().  Handles are internally serialised (one mutex + one CUDA stream per
+ * handle), so concurrent calls from Marqo's request threadpool are safe.  There is no CPU
+ * fallback: without a usable sm_100 device every compute entry point fails with
+ * B200_ERR_NO_DEVICE.
+ */
+#ifndef MARQO_B200_H
+#define MARQO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_ABI_VERSION 1
+
+enum b200_status {
+    B200_OK = 0,
+    B200_ERR_INVALID_ARG = 1,
+    B200_ERR_NO_DEVICE = 2,
+    B200_ERR_CUDA = 3,
+    B200_ERR_OOM = 4,
+    B200_ERR_UNSUPPORTED = 5,
+    B200_ERR_INTERNAL = 6,
+    B200_ERR_MISSING_WEIGHT = 7
+};
+
+int b200_abi_version(void);
+/* Thread-local text of the last failure on this thread ("" if none). */
+const char* b200_last_error(void);
+/* Number of visible CUDA devices with compute capability 10.x. */
+int b200_device_count(int* out_count);
+
+/* ===================================================================================== */
+/* Score + top-k over a GPU-resident embedding matrix  (replaces the Vespa   */
+/* nearestNeighbor / closeness / top-k round trip specified by                            */
+/* src/marqo/core/unstructured_vespa_index/unstructured_vespa_index.py:59-133,            */
+/* src/marqo/core/structured_vespa_index/structured_vespa_index.py:403-446,645-688 and    */
+/* src/marqo/core/unstructured_vespa_index/unstructured_vespa_schema.py:155-166,225-230). */
+/* ===================================================================================== */
+
+typedef struct b200_index b200_index;
+
+/* Distance metrics: names from src/marqo/core/models/marqo_index.py:63-69. */
+enum b200_metric {
+    B200_METRIC_PRENORMALIZED_ANGULAR = 0, /* distance = 1 - q.e           closeness = 1/(1+d) */
+    B200_METRIC_ANGULAR = 1,               /* distance = acos(cos(q,e))    closeness = 1/(1+d) */
+    B200_METRIC_DOTPRODUCT = 2,            /* distance = -q.e              closeness = q.e (raw) */
+    B200_METRIC_EUCLIDEAN = 3              /* distance = |q-e|             closeness = 1/(1+d) */
+};
+
+/* Create an empty row store of fp16[capacity_rows, dim] on `device` (grows on demand).
+ * dim must be a multiple of 64 and <= 1024. */
+int b200_index_create(int device, int dim, int metric, int64_t capacity_rows, b200_index** out);
+int b200_index_destroy(b200_index* ix);
+
+/* Append m chunk embeddings (fp32, host, row-major [m, dim]).  doc_ids[i] is the internal
+ * document number (>= 0) the chunk belongs to; NULL means "one chunk per document, document
+ * number == row number".  Rows of one document need not be contiguous.  Replaces
+ * VespaClient.feed_batch for the tensor fields (vespa_client.py:267-296; the per-document
+ * {"<chunk>": [floats]} blocks built at
+ * src/marqo/core/semi_structured_vespa_index/semi_structured_document.py:127-143). */
+int b200_index_add(b200_index* ix, const float* vecs, const int32_t* doc_ids, int64_t m);
+/* Same, source already on the index's device (fp32 [m, dim]); used by the add_documents fast
+ * path that never materialises List[List[float]] on the host. */
+int b200_index_add_device(b200_index* ix, const float* d_vecs, const int32_t* d_doc_ids, int64_t m);
+/* Tombstone every row of a document (add_documents replaces by _id:
+ * src/marqo/core/vespa_index/add_documents_handler.py:140,258). */
+int b200_index_delete_doc(b200_index* ix, int32_t doc_id);
+int b200_index_num_rows(b200_index* ix, int64_t* out_rows);
+int b200_index_info(b200_index* ix, int* out_dim, int* out_metric, int* out_device);
+/* Copy row `row` back as fp32 (get_batch / use_existing_tensors:
+ * add_documents_handler.py:160-165). */
+int b200_index_get_row(b200_index* ix, int64_t row, float* out_vec);
+
+/* Exact search.  q: fp32 host [nq, dim].  For every query returns the k best DOCUMENTS under
+ *   score(doc) = max over the document's live rows of closeness(q, row)
+ * ordered by (score desc, doc_id asc).  out_doc/out_row/out_score are [nq, k]; unused slots are
+ * filled with doc = row = -1, score = -inf.  out_row is the arg-max chunk row (Vespa's
+ * closest(), used for _highlights: structured_vespa_index.py:942-1000).  out_score is the
+ * closeness ("relevance", tensor_search.py:1771-1791) computed in fp64 from an exactly
+ * rescored dot product. */
+int b200_index_search(b200_index* ix, const float* q, int nq, int k, int32_t* out_doc, int32_t* out_row,
+                      double* out_score);
+/* Same with queries and outputs resident on the index's device; asynchronous on the handle's
+ * stream unless sync != 0. */
+int b200_index_search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_out_doc,
+                             int32_t* d_out_row, double* d_out_score, int sync);
+/* Device time (ms, CUDA events on the handle's stream) of the scan / merge kernels of the last
+ * search call; used by bench.py for the roofline numerator. */
+int b200_index_last_timing(b200_index* ix, float* scan_ms, float* merge_ms);
+/* Merge `nshards` per-shard result lists ([nshards, nq, k] each, host) into the global top-k
+ * with the same total order; doc ids must already be global.  Used after the NCCL all-gather
+ * of per-shard lists. */
+int b200_topk_merge(int nshards, int nq, int k, const int32_t* doc, const int32_t* row, const double* score,
+                    int32_t* out_doc, int32_t* out_row, double* out_score);
+/* Binary snapshot of the row store (persistence / restart). */
+int b200_index_save(b200_index* ix, const char* path);
+int b200_index_load(int device, const char* path, b200_index** out);
+
+/* ===================================================================================== */
+/* Encoders: CLIP ViT image tower, CLIP text tower, BERT (e5).          */
+/* Replace model.encode_image / encode_text / AutoModel forward called at                 */
+/* src/marqo/core/inference/embedding_models/open_clip_model.py:249-286 and               */
+/* src/marqo/core/inference/embedding_models/hugging_face_model.py:172-214.               */
+/* ===================================================================================== */
+
+typedef struct b200_model b200_model;
+
+enum b200_arch {
+    B200_ARCH_CLIP = 0, /* open_clip CLIP: vision tower + text tower */
+    B200_ARCH_BERT = 1  /* HF BertModel + pooling */
+};
+enum b200_act { B200_ACT_GELU = 0, B200_ACT_QUICKGELU = 1 };
+enum b200_pool { B200_POOL_MEAN = 0, B200_POOL_CLS = 1 };
+
+typedef struct b200_tower_desc {
+    int32_t width;      /* hidden size */
+    int32_t layers;     /* transformer blocks */
+    int32_t heads;      /* head_dim = width / heads must be 64 */
+    int32_t mlp;        /* MLP hidden size */
+    int32_t ctx;        /* text: context length (77 / 512); vision: unused */
+    int32_t vocab;      /* text: vocabulary size; vision: unused */
+    int32_t image_size; /* vision: 224 */
+    int32_t patch;      /* vision: 32 / 14 */
+} b200_tower_desc;
+
+typedef struct b200_model_desc {
+    int32_t arch;      /* enum b200_arch */
+    int32_t embed_dim; /* output dimension (CLIP projection dim; BERT: == width) */
+    int32_t act;       /* enum b200_act */
+    int32_t pool;      /* BERT only: enum b200_pool (hugging_face_model.py:205-214) */
+    int32_t type_vocab; /* BERT only: token_type vocabulary (2) */
+    int32_t max_batch; /* workspace sizing: largest number of items per encode call */
+    float image_mean[3]; /* Normalize() constants, src/marqo/s2_inference/clip_utils.py:32-33 */
+    float image_std[3];
+    b200_tower_desc vision; /* CLIP only */
+    b200_tower_desc text;   /* CLIP text tower, or the BERT encoder */
+} b200_model_desc;
+
+int b200_model_create(int device, const b200_model_desc* desc, b200_model** out);
+int b200_model_destroy(b200_model* m);
+/* Upload one parameter (fp32, host, contiguous) under its checkpoint name: open_clip
+ * state_dict names for CLIP ("visual.conv1.weight", "transformer.resblocks.0.attn.in_proj_weight",
+ * ...), HF BertModel names for BERT ("embeddings.word_embeddings.weight", ...). */
+int b200_model_load_tensor(b200_model* m, const char* name, const float* data, int64_t numel);
+/* Verifies every required parameter has been supplied, builds derived buffers. */
+int b200_model_finalize(b200_model* m);
+
+/* Images as uint8 HWC (host), all n of size h x w: resize (bicubic, shortest side) ->
+ * centre-crop -> /255 -> Normalize -> ViT -> proj -> optional L2 normalise.
+ * Replaces preprocessors['image'](pil).to(device) (src/marqo/tensor_search/add_docs.py:129-134)
+ * + OPEN_CLIP.encode_image (open_clip_model.py:249-266).  out: fp32 host [n, embed_dim]. */
+int b200_model_encode_images_u8(b200_model* m, const uint8_t* hwc, int n, int h, int w, int normalize,
+                                float* out);
+/* Already-preprocessed fp32 CHW tensors [n,3,S,S] (the reference passes these through
+ * unchanged: abstract_clip_model.py:108-111). */
+int b200_model_encode_images_f32(b200_model* m, const float* chw, int n, int normalize, float* out);
+/* Token ids int32 [n, seq] (host).  CLIP: causal text tower, EOT = arg-max id pooling.
+ * BERT: attn_mask int32 [n, seq] (1 = token, 0 = pad; NULL = all ones), token_type 0. */
+int b200_model_encode_tokens(b200_model* m, const int32_t* ids, const int32_t* attn_mask, int n, int seq,
+                             int normalize, float* out);
+/* Device-resident variants: inputs/outputs are device pointers on the model's device,
+ * asynchronous on the model's stream unless sync != 0. */
+int b200_model_encode_images_u8_device(b200_model* m, const uint8_t* d_hwc, int n, int h, int w, int normalize,
+                                       float* d_out, int sync);
+int b200_model_encode_tokens_device(b200_model* m, const int32_t* d_ids, const int32_t* d_attn_mask, int n,
+                                    int seq, int normalize, float* d_out, int sync);
+/* Device time (ms) of the last encode call and the number of kernels it launched. */
+int b200_model_last_timing(b200_model* m, float* ms, int* launches);
+
+/* Weighted-mean fusion + renormalise on the host-side contract of
+ * src/marqo/tensor_search/tensor_search.py:1953-1973 and
+ * src/marqo/core/inference/tensor_fields_container.py:355-365:
+ * out = mean_i(w_i * v_i); if normalize and |out| > 0: out /= |out|.  fp64 arithmetic. */
+int b200_fuse_vectors(const double* vecs, const double* weights, int n, int dim, int normalize, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARQO_B200_H */

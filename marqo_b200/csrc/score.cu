@@ -1,0 +1,1010 @@
+// Score + top-k over a GPU-resident fp16 embedding matrix.
+//
+// Reference semantics (executed inside Vespa today, specified by
+// src/marqo/core/unstructured_vespa_index/unstructured_vespa_index.py:59-133 and the rank profile in
+// src/marqo/core/unstructured_vespa_index/unstructured_vespa_schema.py:225-230,292-294):
+//   score(doc) = max over the doc's chunk rows of closeness(q, row);  top-`hits` documents.
+//
+// Pipeline per group of <= 64 queries:
+//   1. scan_kernel   persistent, one CTA per SM.  The corpus is streamed once from HBM by TMA (128-byte
+//                    swizzle, 16 KB stages) and multiplied against the smem-resident query block with
+//                    tcgen05.mma (M = 64 queries, N = 128 rows, fp16 x fp16 -> fp32 in TMEM).  Four epilogue
+//                    warps read the accumulators back (TMEM lane == query) and each thread keeps a sorted
+//                    register list of the KP best (score, row, doc) for its query, de-duplicated by document.
+//   2. merge_kernel  one CTA per query: bitonic-sorts the per-CTA lists, de-duplicates documents, then
+//                    RE-SCORES the KP survivors exactly (fp64, fixed summation order — the order
+//                    oracle/score_oracle.c restates) and emits the top-k under (score desc, doc asc).
+// The approximate tensor-core score only selects candidates; ids and scores returned are from the exact pass,
+// which is what makes the ids bit-exact against the oracle.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mb {
+namespace score {
+
+constexpr int TILE_N = 128;     // corpus rows per tile (UMMA_N)
+constexpr int BLOCK_K = 64;     // fp16 elements per 128-byte swizzle row
+constexpr int MQ = 64;          // queries per pass (UMMA_M)
+constexpr int UMMA_K = 16;
+constexpr int KP = 16;          // candidates kept per list
+constexpr int ACC_STAGES = 4;   // TMEM accumulators (4 x 128 fp32 columns = all 512 columns)
+constexpr int THREADS = 192;    // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr uint32_t STAGE_BYTES = TILE_N * BLOCK_K * 2;
+constexpr uint32_t QCHUNK_BYTES = MQ * BLOCK_K * 2;
+constexpr int MAX_DIM = 1024;
+constexpr int SMEM_LIMIT = 232448;  // 227 KB
+
+struct ScanParams {
+    int n_rows;
+    int dim;
+    int num_tiles;
+    int num_stages;
+    int nq;
+    const int32_t* doc_of_row;  // used when HAS_DOCS
+    const float* bound_score;   // optional [MQ]: only rows strictly after (bound_score, bound_row) qualify
+    const int32_t* bound_row;
+    float* out_score;           // [grid][MQ][KP]
+    int32_t* out_row;
+    int32_t* out_doc;
+};
+
+__host__ __device__ inline size_t scan_smem_bytes(int dim, int stages) {
+    return (size_t)(dim / BLOCK_K) * QCHUNK_BYTES + (size_t)stages * STAGE_BYTES + 4 * TILE_N * sizeof(int32_t) +
+           (2 * 16 + 2 * ACC_STAGES + 2) * sizeof(uint64_t) + 1024 /* alignment slack */;
+}
+
+__device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int t = 0; t < 32; ++t)
+        if (t == j) r = v[t];
+    return __uint_as_float(r);
+}
+
+// Sorted (score desc, arrival order) list insert with per-document de-duplication.
+template <bool HAS_DOCS>
+__device__ __forceinline__ void list_insert(float (&ls)[KP], int (&lr)[KP], int (&ld)[KP], float s, int row, int doc) {
+    if (HAS_DOCS) {
+        int pos = -1;
+#pragma unroll
+        for (int i = 0; i < KP; ++i)
+            if (lr[i] >= 0 && ld[i] == doc) pos = i;
+        if (pos >= 0) {
+            float old = 0.f;
+#pragma unroll
+            for (int i = 0; i < KP; ++i)
+                if (i == pos) old = ls[i];
+            if (old >= s) return;  // the document is already listed with a better (or equal, earlier) chunk
+#pragma unroll
+            for (int i = 0; i < KP - 1; ++i)
+                if (i >= pos) {
+                    ls[i] = ls[i + 1];
+                    lr[i] = lr[i + 1];
+                    ld[i] = ld[i + 1];
+                }
+            ls[KP - 1] = -INFINITY;
+            lr[KP - 1] = -1;
+            ld[KP - 1] = -1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KP; ++i) {
+        if (s > ls[i]) {
+            float ts = ls[i];
+            int tr = lr[i], td = ld[i];
+            ls[i] = s;
+            lr[i] = row;
+            ld[i] = doc;
+            s = ts;
+            row = tr;
+            doc = td;
+        }
+    }
+}
+
+template <bool HAS_DOCS>
+__global__ void __launch_bounds__(THREADS, 1)
+scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_q, ScanParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int kblocks = p.dim / BLOCK_K;
+    const int S = p.num_stages;
+    uint8_t* smem_q = smem;
+    uint8_t* smem_c = smem_q + (size_t)kblocks * QCHUNK_BYTES;
+    int32_t* smem_docs = reinterpret_cast<int32_t*>(smem_c + (size_t)S * STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_docs + 4 * TILE_N);
+    uint64_t* empty = full + 16;
+    uint64_t* tfull = empty + 16;
+    uint64_t* tempty = tfull + ACC_STAGES;
+    uint64_t* qfull = tempty + ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qfull + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_c);
+        ptx::prefetch_tmap(&tmap_q);
+        for (int i = 0; i < S; ++i) {
+            ptx::mbar_init(&full[i], 1);
+            ptx::mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < ACC_STAGES; ++i) {
+            ptx::mbar_init(&tfull[i], 1);
+            ptx::mbar_init(&tempty[i], 4);
+        }
+        ptx::mbar_init(qfull, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(qfull, kblocks * QCHUNK_BYTES);
+            for (int kb = 0; kb < kblocks; ++kb)
+                ptx::tma_load_2d(smem_q + (size_t)kb * QCHUNK_BYTES, &tmap_q, qfull, kb * BLOCK_K, 0, ptx::kEvictLast);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                    ptx::tma_load_2d(smem_c + (size_t)stage * STAGE_BYTES, &tmap_c, &full[stage], kb * BLOCK_K,
+                                     tile * TILE_N, ptx::kEvictFirst);
+                    if (++stage == S) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        ptx::mbar_wait(qfull, 0);
+        ptx::tc_fence_after();
+        constexpr uint32_t idesc = ptx::make_idesc_f16(0 /*fp16*/, MQ, TILE_N);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+            ptx::tc_fence_after();
+            for (int kb = 0; kb < kblocks; ++kb) {
+                ptx::mbar_wait(&full[stage], phase);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_base = ptx::smem_u32(smem_q + (size_t)kb * QCHUNK_BYTES);
+                    const uint32_t b_base = ptx::smem_u32(smem_c + (size_t)stage * STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        ptx::umma_f16(tmem_base + acc * TILE_N, ptx::make_desc_k_sw128(a_base + k * UMMA_K * 2),
+                                      ptx::make_desc_k_sw128(b_base + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit(&empty[stage]);
+                    if (kb == kblocks - 1) ptx::umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (++acc == ACC_STAGES) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: per-query running top-KP
+        const int sp = warp & 3;  // TMEM sub-partition this warp may read
+        const int q = sp * 16 + lane;  // M = 64 accumulator: row m lives in lane (m % 16) of sub-partition m / 16
+        const bool active = lane < 16 && q < p.nq;
+        int32_t* my_docs = smem_docs + (warp - 2) * TILE_N;
+        float ls[KP];
+        int lr[KP], ld[KP];
+#pragma unroll
+        for (int i = 0; i < KP; ++i) {
+            ls[i] = -INFINITY;
+            lr[i] = -1;
+            ld[i] = -1;
+        }
+        float thr = -INFINITY;
+        const bool bounded = p.bound_score != nullptr;
+        float bs = INFINITY;
+        int br = -1;
+        if (bounded && active) {
+            bs = p.bound_score[q];
+            br = p.bound_row[q];
+        }
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+            const int row0 = tile * TILE_N;
+            if (HAS_DOCS) {
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    int r = row0 + t * 32 + lane;
+                    my_docs[t * 32 + lane] = r < p.n_rows ? __ldg(p.doc_of_row + r) : -1;
+                }
+                __syncwarp();
+            }
+            ptx::mbar_wait(&tfull[acc], acc_phase);
+            ptx::tc_fence_after();
+            const int valid = min(TILE_N, p.n_rows - row0);
+#pragma unroll 1
+            for (int c = 0; c < TILE_N / 32; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(sp * 32) << 16) + acc * TILE_N + c * 32, v);
+                ptx::tmem_ld_wait();
+                if (active) {
+                    uint32_t mask = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
+                    const int nvalid = valid - c * 32;
+                    if (nvalid < 32) mask &= nvalid <= 0 ? 0u : ((1u << nvalid) - 1u);
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float s = pick32(v, j);
+                        const int row = row0 + c * 32 + j;
+                        if (!(s > thr)) continue;
+                        if (bounded && !(s < bs || (s == bs && row > br))) continue;
+                        int doc = row;
+                        if (HAS_DOCS) {
+                            doc = my_docs[c * 32 + j];
+                            if (doc < 0) continue;  // tombstoned row
+                        }
+                        list_insert<HAS_DOCS>(ls, lr, ld, s, row, doc);
+                        thr = ls[KP - 1];
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+            if (++acc == ACC_STAGES) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+        if (lane < 16) {
+            const size_t base = ((size_t)blockIdx.x * MQ + q) * KP;
+#pragma unroll
+            for (int i = 0; i < KP; ++i) {
+                p.out_score[base + i] = ls[i];
+                p.out_row[base + i] = lr[i];
+                p.out_doc[base + i] = ld[i];
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct MergeParams {
+    int num_lists;  // scan grid size
+    int nq;
+    int k;
+    int dim;
+    int metric;
+    int sort_n;  // power of two >= num_lists * KP
+    const float* in_score;
+    const int32_t* in_row;
+    const int32_t* in_doc;
+    const __half* qh;      // [MQ, dim] fp16 queries as scanned
+    const __half* corpus;  // [n_rows, dim]
+    int32_t* out_doc;      // [nq, k]
+    int32_t* out_row;
+    double* out_score;
+    // optional candidate dump for multi-round search: [nq][KP] sorted by (approx desc, row asc)
+    float* cand_score;
+    int32_t* cand_row;
+};
+
+__device__ __forceinline__ bool approx_before(float sa, int ra, float sb, int rb) {
+    return sa > sb || (sa == sb && ra < rb);
+}
+
+__device__ __forceinline__ double closeness_from_dot(double dot, int metric) {
+    switch (metric) {
+        case B200_METRIC_PRENORMALIZED_ANGULAR:
+            return 1.0 / (1.0 + (1.0 - dot));
+        case B200_METRIC_ANGULAR: {
+            double c = fmin(1.0, fmax(-1.0, dot));
+            return 1.0 / (1.0 + acos(c));
+        }
+        default:
+            return dot;
+    }
+}
+
+constexpr int MERGE_THREADS = 256;
+
+__global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeParams p) {
+    extern __shared__ uint8_t msmem[];
+    float* s_score = reinterpret_cast<float*>(msmem);
+    int32_t* s_row = reinterpret_cast<int32_t*>(s_score + p.sort_n);
+    int32_t* s_doc = s_row + p.sort_n;
+    __shared__ int sel_row[KP], sel_doc[KP], sel_n;
+    __shared__ double sel_dot[KP];
+
+    const int q = blockIdx.x;
+    const int total = p.num_lists * KP;
+    for (int i = threadIdx.x; i < p.sort_n; i += blockDim.x) {
+        float s = -INFINITY;
+        int r = INT_MAX, d = -1;
+        if (i < total) {
+            const int list = i / KP, e = i % KP;
+            const size_t src = ((size_t)list * MQ + q) * KP + e;
+            const int rr = p.in_row[src];
+            if (rr >= 0) {
+                s = p.in_score[src];
+                r = rr;
+                d = p.in_doc[src];
+            }
+        }
+        s_score[i] = s;
+        s_row[i] = r;
+        s_doc[i] = d;
+    }
+    __syncthreads();
+    // bitonic sort, order: (score desc, row asc)
+    for (int size = 2; size <= p.sort_n; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < p.sort_n / 2; i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const float sa = s_score[lo], sb = s_score[hi];
+                const int ra = s_row[lo], rb = s_row[hi];
+                const bool wrong = up ? approx_before(sb, rb, sa, ra) : approx_before(sa, ra, sb, rb);
+                if (wrong) {
+                    s_score[lo] = sb;
+                    s_score[hi] = sa;
+                    s_row[lo] = rb;
+                    s_row[hi] = ra;
+                    const int da = s_doc[lo];
+                    s_doc[lo] = s_doc[hi];
+                    s_doc[hi] = da;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int i = 0; i < total && n < KP; ++i) {
+            if (s_row[i] == INT_MAX) break;
+            const int d = s_doc[i];
+            bool dup = false;
+            for (int j = 0; j < n; ++j) dup |= (sel_doc[j] == d);
+            if (dup) continue;
+            sel_row[n] = s_row[i];
+            sel_doc[n] = d;
+            if (p.cand_score) {
+                p.cand_score[(size_t)q * KP + n] = s_score[i];
+                p.cand_row[(size_t)q * KP + n] = s_row[i];
+            }
+            ++n;
+        }
+        if (p.cand_score)
+            for (int i = n; i < KP; ++i) {
+                p.cand_score[(size_t)q * KP + i] = -INFINITY;
+                p.cand_row[(size_t)q * KP + i] = -1;
+            }
+        sel_n = n;
+    }
+    __syncthreads();
+    // exact re-score: lane l accumulates elements i = 32 j + l in ascending j (fp64), partials are then added in
+    // ascending lane order.  oracle/score_oracle.c restates exactly this order.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = warp; c < sel_n; c += MERGE_THREADS / 32) {
+        const __half* qv = p.qh + (size_t)q * p.dim;
+        const __half* cv = p.corpus + (size_t)sel_row[c] * p.dim;
+        double part = 0.0;
+        for (int i = lane; i < p.dim; i += 32) part += (double)__half2float(qv[i]) * (double)__half2float(cv[i]);
+        double tot = 0.0;
+        for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);
+        if (lane == 0) sel_dot[c] = tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int n = sel_n;
+        // insertion sort by (dot desc, doc asc)
+        for (int i = 1; i < n; ++i) {
+            const double d = sel_dot[i];
+            const int r = sel_row[i], dc = sel_doc[i];
+            int j = i - 1;
+            while (j >= 0 && (sel_dot[j] < d || (sel_dot[j] == d && sel_doc[j] > dc))) {
+                sel_dot[j + 1] = sel_dot[j];
+                sel_row[j + 1] = sel_row[j];
+                sel_doc[j + 1] = sel_doc[j];
+                --j;
+            }
+            sel_dot[j + 1] = d;
+            sel_row[j + 1] = r;
+            sel_doc[j + 1] = dc;
+        }
+        for (int i = 0; i < p.k; ++i) {
+            const size_t o = (size_t)q * p.k + i;
+            if (i < n) {
+                p.out_doc[o] = sel_doc[i];
+                p.out_row[o] = sel_row[i];
+                p.out_score[o] = closeness_from_dot(sel_dot[i], p.metric);
+            } else {
+                p.out_doc[o] = -1;
+                p.out_row[o] = -1;
+                p.out_score[o] = -INFINITY;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 -> fp16 row conversion (optionally L2-normalising first, for the angular metric).
+__global__ void convert_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t rows, int dim,
+                                    int64_t dst_rows_total, int normalize) {
+    // one warp per row; rows in [rows, dst_rows_total) are zero-filled (query padding)
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= dst_rows_total) return;
+    __half* d = dst + row * dim;
+    if (row >= rows) {
+        for (int i = lane; i < dim; i += 32) d[i] = __float2half_rn(0.f);
+        return;
+    }
+    const float* s = src + row * dim;
+    float scale = 1.f;
+    if (normalize) {
+        float ss = 0.f;
+        for (int i = lane; i < dim; i += 32) ss = __fmaf_rn(s[i], s[i], ss);
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        scale = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
+    }
+    for (int i = lane; i < dim; i += 32) d[i] = __float2half_rn(s[i] * scale);
+}
+
+__global__ void iota_kernel(int32_t* dst, int64_t n, int32_t start) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = start + (int32_t)i;
+}
+
+__global__ void tombstone_kernel(int32_t* doc_of_row, int64_t n, int32_t doc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && doc_of_row[i] == doc) doc_of_row[i] = -1;
+}
+
+__global__ void fill_empty_kernel(int32_t* out_doc, int32_t* out_row, double* out_score, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        out_doc[i] = -1;
+        out_row[i] = -1;
+        out_score[i] = -INFINITY;
+    }
+}
+
+}  // namespace score
+}  // namespace mb
+
+// ====================================================================================================
+using namespace mb;
+using namespace mb::score;
+
+struct b200_index {
+    int device = 0;
+    int dim = 0;
+    int metric = 0;
+    int sms = 0;
+    int64_t capacity = 0;
+    int64_t n_rows = 0;
+    bool has_docs = false;  // false while doc_of_row[i] == i for every row (identity fast path)
+    __half* corpus = nullptr;
+    int32_t* doc_of_row = nullptr;
+    // per-search workspaces
+    __half* qh = nullptr;          // [MQ, dim]
+    float* q_stage = nullptr;      // [MQ, dim] fp32 staging for host queries
+    float* list_score = nullptr;   // [sms][MQ][KP]
+    int32_t* list_row = nullptr;
+    int32_t* list_doc = nullptr;
+    int32_t* o_doc = nullptr;      // [MQ, KP] device outputs for the host API
+    int32_t* o_row = nullptr;
+    double* o_score = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool timing_valid = false;
+    std::mutex mu;
+};
+
+namespace {
+
+void index_free(b200_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaFree(ix->corpus);
+    cudaFree(ix->doc_of_row);
+    cudaFree(ix->qh);
+    cudaFree(ix->q_stage);
+    cudaFree(ix->list_score);
+    cudaFree(ix->list_row);
+    cudaFree(ix->list_doc);
+    cudaFree(ix->o_doc);
+    cudaFree(ix->o_row);
+    cudaFree(ix->o_score);
+    for (auto& e : ix->ev)
+        if (e) cudaEventDestroy(e);
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+void cuda_alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        fail(B200_ERR_OOM, "cudaMalloc(%zu bytes) failed: out of device memory", bytes);
+    }
+    MB_CUDA(e);
+}
+
+void ensure_capacity(b200_index* ix, int64_t need_rows) {
+    if (need_rows <= ix->capacity) return;
+    int64_t cap = std::max<int64_t>(need_rows, ix->capacity + ix->capacity / 2);
+    cap = (int64_t)round_up((size_t)cap, TILE_N);
+    __half* nc = nullptr;
+    int32_t* nd = nullptr;
+    cuda_alloc((void**)&nc, (size_t)cap * ix->dim * sizeof(__half));
+    cuda_alloc((void**)&nd, (size_t)cap * sizeof(int32_t));
+    if (ix->n_rows > 0) {
+        MB_CUDA(cudaMemcpyAsync(nc, ix->corpus, (size_t)ix->n_rows * ix->dim * sizeof(__half), cudaMemcpyDeviceToDevice,
+                                ix->stream));
+        MB_CUDA(cudaMemcpyAsync(nd, ix->doc_of_row, (size_t)ix->n_rows * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                ix->stream));
+    }
+    MB_CUDA(cudaStreamSynchronize(ix->stream));
+    cudaFree(ix->corpus);
+    cudaFree(ix->doc_of_row);
+    ix->corpus = nc;
+    ix->doc_of_row = nd;
+    ix->capacity = cap;
+}
+
+b200_index* index_new(int device, int dim, int metric, int64_t capacity_rows) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        fail(B200_ERR_NO_DEVICE, "no CUDA device available (marqo_b200 has no CPU fallback)");
+    }
+    MB_CHECK_ARG(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+    int major = 0;
+    MB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) fail(B200_ERR_NO_DEVICE, "device %d has compute capability %d.x; sm_100 required", device, major);
+    MB_CHECK_ARG(dim > 0 && dim % BLOCK_K == 0 && dim <= MAX_DIM, "dim must be a multiple of %d and <= %d (got %d)",
+                 BLOCK_K, MAX_DIM, dim);
+    MB_CHECK_ARG(metric >= 0 && metric <= B200_METRIC_EUCLIDEAN, "unknown metric %d", metric);
+    if (metric == B200_METRIC_EUCLIDEAN) fail(B200_ERR_UNSUPPORTED, "euclidean metric is not implemented yet");
+    MB_CHECK_ARG(capacity_rows >= 0, "capacity_rows must be >= 0");
+    DeviceGuard g(device);
+    b200_index* ix = new b200_index();
+    try {
+        ix->device = device;
+        ix->dim = dim;
+        ix->metric = metric;
+        ix->sms = sm_count(device);
+        MB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+        for (auto& e : ix->ev) MB_CUDA(cudaEventCreate(&e));
+        cuda_alloc((void**)&ix->qh, (size_t)MQ * dim * sizeof(__half));
+        cuda_alloc((void**)&ix->q_stage, (size_t)MQ * dim * sizeof(float));
+        const size_t nl = (size_t)ix->sms * MQ * KP;
+        cuda_alloc((void**)&ix->list_score, nl * sizeof(float));
+        cuda_alloc((void**)&ix->list_row, nl * sizeof(int32_t));
+        cuda_alloc((void**)&ix->list_doc, nl * sizeof(int32_t));
+        cuda_alloc((void**)&ix->o_doc, (size_t)MQ * KP * sizeof(int32_t));
+        cuda_alloc((void**)&ix->o_row, (size_t)MQ * KP * sizeof(int32_t));
+        cuda_alloc((void**)&ix->o_score, (size_t)MQ * KP * sizeof(double));
+        ensure_capacity(ix, std::max<int64_t>(capacity_rows, TILE_N));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    } catch (...) {
+        index_free(ix);
+        throw;
+    }
+    return ix;
+}
+
+void add_rows_device(b200_index* ix, const float* d_vecs, const int32_t* d_doc_ids, int64_t m) {
+    ensure_capacity(ix, ix->n_rows + m);
+    const int wpb = 8;
+    const int64_t blocks = (m + wpb - 1) / wpb;
+    convert_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, ix->stream>>>(
+        d_vecs, ix->corpus + (size_t)ix->n_rows * ix->dim, m, ix->dim, m, ix->metric == B200_METRIC_ANGULAR);
+    MB_CUDA(cudaGetLastError());
+    if (d_doc_ids) {
+        MB_CUDA(cudaMemcpyAsync(ix->doc_of_row + ix->n_rows, d_doc_ids, (size_t)m * sizeof(int32_t),
+                                cudaMemcpyDeviceToDevice, ix->stream));
+        ix->has_docs = true;
+    } else {
+        iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, ix->stream>>>(ix->doc_of_row + ix->n_rows, m,
+                                                                        (int32_t)ix->n_rows);
+        MB_CUDA(cudaGetLastError());
+    }
+    ix->n_rows += m;
+}
+
+// One pass over the corpus for <= MQ queries already converted into ix->qh.
+void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_out_row, double* d_out_score,
+                  bool record_timing) {
+    const int total = nq * k;
+    if (ix->n_rows == 0) {
+        fill_empty_kernel<<<(total + 255) / 256, 256, 0, ix->stream>>>(d_out_doc, d_out_row, d_out_score, total);
+        MB_CUDA(cudaGetLastError());
+        return;
+    }
+    const int num_tiles = (int)((ix->n_rows + TILE_N - 1) / TILE_N);
+    const int grid = std::min(num_tiles, ix->sms);
+    int stages = 16;
+    while (stages > 2 && scan_smem_bytes(ix->dim, stages) > (size_t)SMEM_LIMIT) --stages;
+    const size_t smem = scan_smem_bytes(ix->dim, stages);
+    if (smem > (size_t)SMEM_LIMIT) fail(B200_ERR_INTERNAL, "scan kernel shared memory budget exceeded");
+
+    CUtensorMap tmap_c = make_tmap_2d(ix->corpus, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)ix->dim,
+                                      (uint64_t)ix->n_rows, (uint64_t)ix->dim * 2, BLOCK_K, TILE_N,
+                                      CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tmap_q = make_tmap_2d(ix->qh, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)ix->dim, (uint64_t)MQ,
+                                      (uint64_t)ix->dim * 2, BLOCK_K, MQ, CU_TENSOR_MAP_SWIZZLE_128B);
+    ScanParams sp{};
+    sp.n_rows = (int)ix->n_rows;
+    sp.dim = ix->dim;
+    sp.num_tiles = num_tiles;
+    sp.num_stages = stages;
+    sp.nq = nq;
+    sp.doc_of_row = ix->doc_of_row;
+    sp.bound_score = nullptr;
+    sp.bound_row = nullptr;
+    sp.out_score = ix->list_score;
+    sp.out_row = ix->list_row;
+    sp.out_doc = ix->list_doc;
+
+    if (record_timing) MB_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
+    if (ix->has_docs)
+        scan_kernel<true><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
+    else
+        scan_kernel<false><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
+    MB_CUDA(cudaGetLastError());
+    if (record_timing) MB_CUDA(cudaEventRecord(ix->ev[1], ix->stream));
+
+    MergeParams mp{};
+    mp.num_lists = grid;
+    mp.nq = nq;
+    mp.k = k;
+    mp.dim = ix->dim;
+    mp.metric = ix->metric;
+    int sort_n = 32;
+    while (sort_n < grid * KP) sort_n <<= 1;
+    mp.sort_n = sort_n;
+    mp.in_score = ix->list_score;
+    mp.in_row = ix->list_row;
+    mp.in_doc = ix->list_doc;
+    mp.qh = ix->qh;
+    mp.corpus = ix->corpus;
+    mp.out_doc = d_out_doc;
+    mp.out_row = d_out_row;
+    mp.out_score = d_out_score;
+    mp.cand_score = nullptr;
+    mp.cand_row = nullptr;
+    merge_kernel<<<nq, MERGE_THREADS, (size_t)sort_n * 12, ix->stream>>>(mp);
+    MB_CUDA(cudaGetLastError());
+    if (record_timing) {
+        MB_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
+        ix->timing_valid = true;
+    }
+}
+
+void search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_out_doc, int32_t* d_out_row,
+                   double* d_out_score) {
+    for (int q0 = 0; q0 < nq; q0 += MQ) {
+        const int g = std::min(MQ, nq - q0);
+        convert_rows_kernel<<<MQ / 8, 256, 0, ix->stream>>>(d_q + (size_t)q0 * ix->dim, ix->qh, g, ix->dim, MQ,
+                                                            ix->metric == B200_METRIC_ANGULAR);
+        MB_CUDA(cudaGetLastError());
+        search_group(ix, g, k, d_out_doc + (size_t)q0 * k, d_out_row + (size_t)q0 * k, d_out_score + (size_t)q0 * k,
+                     q0 + MQ >= nq);
+    }
+}
+
+void check_search_args(b200_index* ix, const void* q, int nq, int k, const void* a, const void* b, const void* c) {
+    MB_CHECK_ARG(ix != nullptr, "index is NULL");
+    MB_CHECK_ARG(q && a && b && c, "NULL buffer");
+    MB_CHECK_ARG(nq > 0, "nq must be positive (got %d)", nq);
+    MB_CHECK_ARG(k > 0, "k must be positive (got %d)", k);
+    if (k > KP) fail(B200_ERR_UNSUPPORTED, "k = %d exceeds the single-pass limit of %d", k, KP);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_index_create(int device, int dim, int metric, int64_t capacity_rows, b200_index** out) {
+    return guarded([&] {
+        MB_CHECK_ARG(out != nullptr, "out is NULL");
+        *out = nullptr;
+        *out = index_new(device, dim, metric, capacity_rows);
+    });
+}
+
+int b200_index_destroy(b200_index* ix) {
+    return guarded([&] { index_free(ix); });
+}
+
+int b200_index_add(b200_index* ix, const float* vecs, const int32_t* doc_ids, int64_t m) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix != nullptr, "index is NULL");
+        MB_CHECK_ARG(m >= 0, "m must be >= 0");
+        if (m == 0) return;
+        MB_CHECK_ARG(vecs != nullptr, "vecs is NULL");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        MB_CHECK_ARG(ix->n_rows + m < (int64_t)INT32_MAX, "row count would exceed 2^31-1");
+        if (doc_ids)
+            for (int64_t i = 0; i < m; ++i) MB_CHECK_ARG(doc_ids[i] >= 0, "doc_ids[%lld] is negative", (long long)i);
+        // When explicit ids are given but the index has been identity-mapped so far, the ids must be honoured.
+        float* d_v = nullptr;
+        int32_t* d_d = nullptr;
+        const int64_t chunk = 1 << 16;
+        cuda_alloc((void**)&d_v, (size_t)std::min(m, chunk) * ix->dim * sizeof(float));
+        if (doc_ids) cuda_alloc((void**)&d_d, (size_t)std::min(m, chunk) * sizeof(int32_t));
+        try {
+            for (int64_t o = 0; o < m; o += chunk) {
+                const int64_t c = std::min(chunk, m - o);
+                MB_CUDA(cudaMemcpyAsync(d_v, vecs + (size_t)o * ix->dim, (size_t)c * ix->dim * sizeof(float),
+                                        cudaMemcpyHostToDevice, ix->stream));
+                if (doc_ids)
+                    MB_CUDA(cudaMemcpyAsync(d_d, doc_ids + o, (size_t)c * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                            ix->stream));
+                add_rows_device(ix, d_v, doc_ids ? d_d : nullptr, c);
+                MB_CUDA(cudaStreamSynchronize(ix->stream));
+            }
+        } catch (...) {
+            cudaFree(d_v);
+            cudaFree(d_d);
+            throw;
+        }
+        cudaFree(d_v);
+        cudaFree(d_d);
+    });
+}
+
+int b200_index_add_device(b200_index* ix, const float* d_vecs, const int32_t* d_doc_ids, int64_t m) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix != nullptr, "index is NULL");
+        MB_CHECK_ARG(m >= 0, "m must be >= 0");
+        if (m == 0) return;
+        MB_CHECK_ARG(d_vecs != nullptr, "d_vecs is NULL");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        MB_CHECK_ARG(ix->n_rows + m < (int64_t)INT32_MAX, "row count would exceed 2^31-1");
+        add_rows_device(ix, d_vecs, d_doc_ids, m);
+        MB_CUDA(cudaStreamSynchronize(ix->stream));
+    });
+}
+
+int b200_index_delete_doc(b200_index* ix, int32_t doc_id) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix != nullptr, "index is NULL");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        if (ix->n_rows == 0) return;
+        tombstone_kernel<<<(unsigned)((ix->n_rows + 255) / 256), 256, 0, ix->stream>>>(ix->doc_of_row, ix->n_rows,
+                                                                                      doc_id);
+        MB_CUDA(cudaGetLastError());
+        MB_CUDA(cudaStreamSynchronize(ix->stream));
+        ix->has_docs = true;
+    });
+}
+
+int b200_index_num_rows(b200_index* ix, int64_t* out_rows) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix && out_rows, "NULL argument");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        *out_rows = ix->n_rows;
+    });
+}
+
+int b200_index_info(b200_index* ix, int* out_dim, int* out_metric, int* out_device) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix && out_dim && out_metric && out_device, "NULL argument");
+        *out_dim = ix->dim;
+        *out_metric = ix->metric;
+        *out_device = ix->device;
+    });
+}
+
+int b200_index_get_row(b200_index* ix, int64_t row, float* out_vec) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix && out_vec, "NULL argument");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        MB_CHECK_ARG(row >= 0 && row < ix->n_rows, "row %lld out of range", (long long)row);
+        std::vector<__half> tmp(ix->dim);
+        MB_CUDA(cudaMemcpyAsync(tmp.data(), ix->corpus + (size_t)row * ix->dim, (size_t)ix->dim * sizeof(__half),
+                                cudaMemcpyDeviceToHost, ix->stream));
+        MB_CUDA(cudaStreamSynchronize(ix->stream));
+        for (int i = 0; i < ix->dim; ++i) out_vec[i] = __half2float(tmp[i]);
+    });
+}
+
+int b200_index_search(b200_index* ix, const float* q, int nq, int k, int32_t* out_doc, int32_t* out_row,
+                      double* out_score) {
+    return guarded([&] {
+        check_search_args(ix, q, nq, k, out_doc, out_row, out_score);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        for (int q0 = 0; q0 < nq; q0 += MQ) {
+            const int gq = std::min(MQ, nq - q0);
+            MB_CUDA(cudaMemcpyAsync(ix->q_stage, q + (size_t)q0 * ix->dim, (size_t)gq * ix->dim * sizeof(float),
+                                    cudaMemcpyHostToDevice, ix->stream));
+            search_device(ix, ix->q_stage, gq, k, ix->o_doc, ix->o_row, ix->o_score);
+            MB_CUDA(cudaMemcpyAsync(out_doc + (size_t)q0 * k, ix->o_doc, (size_t)gq * k * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, ix->stream));
+            MB_CUDA(cudaMemcpyAsync(out_row + (size_t)q0 * k, ix->o_row, (size_t)gq * k * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, ix->stream));
+            MB_CUDA(cudaMemcpyAsync(out_score + (size_t)q0 * k, ix->o_score, (size_t)gq * k * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ix->stream));
+            MB_CUDA(cudaStreamSynchronize(ix->stream));
+        }
+    });
+}
+
+int b200_index_search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_out_doc, int32_t* d_out_row,
+                             double* d_out_score, int sync) {
+    return guarded([&] {
+        check_search_args(ix, d_q, nq, k, d_out_doc, d_out_row, d_out_score);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        search_device(ix, d_q, nq, k, d_out_doc, d_out_row, d_out_score);
+        if (sync) MB_CUDA(cudaStreamSynchronize(ix->stream));
+    });
+}
+
+int b200_index_last_timing(b200_index* ix, float* scan_ms, float* merge_ms) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix && scan_ms && merge_ms, "NULL argument");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        if (!ix->timing_valid) fail(B200_ERR_INVALID_ARG, "no search has been timed yet");
+        MB_CUDA(cudaEventSynchronize(ix->ev[2]));
+        MB_CUDA(cudaEventElapsedTime(scan_ms, ix->ev[0], ix->ev[1]));
+        MB_CUDA(cudaEventElapsedTime(merge_ms, ix->ev[1], ix->ev[2]));
+    });
+}
+
+int b200_topk_merge(int nshards, int nq, int k, const int32_t* doc, const int32_t* row, const double* score,
+                    int32_t* out_doc, int32_t* out_row, double* out_score) {
+    return guarded([&] {
+        MB_CHECK_ARG(nshards > 0 && nq > 0 && k > 0, "nshards, nq, k must be positive");
+        MB_CHECK_ARG(doc && row && score && out_doc && out_row && out_score, "NULL buffer");
+        struct Hit {
+            double s;
+            int32_t d, r;
+        };
+        std::vector<Hit> hits;
+        for (int q = 0; q < nq; ++q) {
+            hits.clear();
+            for (int s = 0; s < nshards; ++s)
+                for (int i = 0; i < k; ++i) {
+                    const size_t o = ((size_t)s * nq + q) * k + i;
+                    if (doc[o] >= 0) hits.push_back({score[o], doc[o], row[o]});
+                }
+            std::sort(hits.begin(), hits.end(),
+                      [](const Hit& a, const Hit& b) { return a.s > b.s || (a.s == b.s && a.d < b.d); });
+            for (int i = 0; i < k; ++i) {
+                const size_t o = (size_t)q * k + i;
+                if (i < (int)hits.size()) {
+                    out_doc[o] = hits[i].d;
+                    out_row[o] = hits[i].r;
+                    out_score[o] = hits[i].s;
+                } else {
+                    out_doc[o] = -1;
+                    out_row[o] = -1;
+                    out_score[o] = -std::numeric_limits<double>::infinity();
+                }
+            }
+        }
+    });
+}
+
+int b200_index_save(b200_index* ix, const char* path) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix && path, "NULL argument");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        FILE* f = fopen(path, "wb");
+        if (!f) fail(B200_ERR_INVALID_ARG, "cannot open %s for writing", path);
+        struct {
+            char magic[8];
+            int32_t version, dim, metric, has_docs;
+            int64_t n_rows;
+        } hdr;
+        memcpy(hdr.magic, "B200IDX\0", 8);
+        hdr.version = 1;
+        hdr.dim = ix->dim;
+        hdr.metric = ix->metric;
+        hdr.has_docs = ix->has_docs ? 1 : 0;
+        hdr.n_rows = ix->n_rows;
+        bool ok = fwrite(&hdr, sizeof(hdr), 1, f) == 1;
+        std::vector<uint8_t> buf((size_t)1 << 24);
+        auto dump = [&](const void* dptr, size_t bytes) {
+            for (size_t o = 0; o < bytes && ok; o += buf.size()) {
+                const size_t c = std::min(buf.size(), bytes - o);
+                MB_CUDA(cudaMemcpy(buf.data(), (const uint8_t*)dptr + o, c, cudaMemcpyDeviceToHost));
+                ok = fwrite(buf.data(), 1, c, f) == c;
+            }
+        };
+        MB_CUDA(cudaStreamSynchronize(ix->stream));
+        dump(ix->corpus, (size_t)ix->n_rows * ix->dim * sizeof(__half));
+        dump(ix->doc_of_row, (size_t)ix->n_rows * sizeof(int32_t));
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) fail(B200_ERR_INTERNAL, "short write to %s", path);
+    });
+}
+
+int b200_index_load(int device, const char* path, b200_index** out) {
+    return guarded([&] {
+        MB_CHECK_ARG(path && out, "NULL argument");
+        *out = nullptr;
+        FILE* f = fopen(path, "rb");
+        if (!f) fail(B200_ERR_INVALID_ARG, "cannot open %s", path);
+        struct {
+            char magic[8];
+            int32_t version, dim, metric, has_docs;
+            int64_t n_rows;
+        } hdr;
+        b200_index* ix = nullptr;
+        try {
+            if (fread(&hdr, sizeof(hdr), 1, f) != 1 || memcmp(hdr.magic, "B200IDX\0", 8) != 0 || hdr.version != 1)
+                fail(B200_ERR_INVALID_ARG, "%s is not a marqo_b200 index snapshot", path);
+            ix = index_new(device, hdr.dim, hdr.metric, hdr.n_rows);
+            DeviceGuard g(device);
+            std::vector<uint8_t> buf((size_t)1 << 24);
+            auto slurp = [&](void* dptr, size_t bytes) {
+                for (size_t o = 0; o < bytes; o += buf.size()) {
+                    const size_t c = std::min(buf.size(), bytes - o);
+                    if (fread(buf.data(), 1, c, f) != c) fail(B200_ERR_INVALID_ARG, "%s is truncated", path);
+                    MB_CUDA(cudaMemcpy((uint8_t*)dptr + o, buf.data(), c, cudaMemcpyHostToDevice));
+                }
+            };
+            slurp(ix->corpus, (size_t)hdr.n_rows * hdr.dim * sizeof(__half));
+            slurp(ix->doc_of_row, (size_t)hdr.n_rows * sizeof(int32_t));
+            ix->n_rows = hdr.n_rows;
+            ix->has_docs = hdr.has_docs != 0;
+        } catch (...) {
+            fclose(f);
+            index_free(ix);
+            throw;
+        }
+        fclose(f);
+        *out = ix;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+"""GPU parity tests for the score + top-k path — CUDA path through the C ABI vs oracle/score_oracle.c.
+
+Bar: doc ids and arg-max rows bit-exact; closeness equal to 1e-12 (fp64; acos may differ in the last ulp).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit_rows(rng, n, d):
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    return x
+
+
+def _check(store, so, q, corpus, k, metric, doc_of_row=None):
+    doc, row, score = store.search(q, k)
+    edoc, erow, escore = so.search(q, corpus, k, metric, doc_of_row)
+    np.testing.assert_array_equal(doc, edoc)
+    np.testing.assert_array_equal(row, erow)
+    np.testing.assert_allclose(score, escore, rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("n,d,nq,k", [
+    (1, 64, 1, 1), (7, 64, 3, 10), (128, 128, 64, 10), (129, 256, 5, 3), (1000, 768, 64, 10),
+    (20000, 768, 64, 10), (33333, 512, 17, 16), (5000, 1024, 64, 10), (4097, 384, 100, 10),
+])
+def test_topk_matches_oracle(gpu_required, score_oracle, n, d, nq, k):
+    from marqo_b200.engine import RowStore
+    rng = np.random.default_rng(n * 31 + d)
+    corpus = _unit_rows(rng, n, d)
+    q = _unit_rows(rng, nq, d)
+    store = RowStore(d)
+    store.add(corpus)
+    assert len(store) == n
+    _check(store, score_oracle, q, corpus, k, "prenormalized-angular")
+
+
+def test_self_match_and_duplicates(gpu_required, score_oracle):
+    """queries copied from corpus rows rank first with closeness ~ 1; duplicated rows tie and
+    are returned in ascending doc order (the defined tie rule)."""
+    from marqo_b200.engine import RowStore
+    rng = np.random.default_rng(5)
+    n, d = 30000, 768
+    corpus = _unit_rows(rng, n, d)
+    corpus[20000:20050] = corpus[123]          # 50 exact duplicates of row 123
+    corpus[777] = corpus[29999]
+    q = _unit_rows(rng, 64, d)
+    q[:8] = corpus[[123, 5, 999, 15000, 29999, 4242, 64, 127]]
+    store = RowStore(d)
+    store.add(corpus)
+    doc, row, score = store.search(q, 10)
+    assert doc[0, 0] == 123 and list(doc[0, 1:10]) == list(range(20000, 20009))
+    assert doc[4, 0] == 777 and doc[4, 1] == 29999
+    assert np.all(np.abs(score[:8, 0] - 1.0) < 2e-3)
+    _check(store, score_oracle, q, corpus, 10, "prenormalized-angular")
+
+
+@pytest.mark.parametrize("metric", ["angular", "dotproduct"])
+def test_other_metrics(gpu_required, score_oracle, metric):
+    from marqo_b200.engine import RowStore
+    rng = np.random.default_rng(9)
+    corpus = rng.standard_normal((3000, 256)).astype(np.float32)
+    q = rng.standard_normal((9, 256)).astype(np.float32)
+    store = RowStore(256, metric=metric)
+    store.add(corpus)
+    _check(store, score_oracle, q, corpus, 10, metric)
+
+
+def test_max_over_chunks_and_delete(gpu_required, score_oracle):
+    """score(doc) = max over chunks (unstructured_vespa_schema.py:225-230); deleted docs never surface."""
+    from marqo_b200.engine import RowStore
+    rng = np.random.default_rng(11)
+    n, d = 9000, 256
+    corpus = _unit_rows(rng, n, d)
+    doc_of_row = (np.arange(n) // 3).astype(np.int32)            # 3 chunks per doc
+    doc_of_row[6000:] = rng.integers(0, 3000, size=3000)          # plus scattered extra chunks
+    q = _unit_rows(rng, 40, d)
+    q[0] = corpus[4]                                              # doc 1, chunk row 4
+    store = RowStore(d)
+    store.add(corpus[:5000], doc_of_row[:5000])
+    store.add(corpus[5000:], doc_of_row[5000:])
+    doc, row, score = store.search(q, 10)
+    assert doc[0, 0] == 1 and row[0, 0] == 4
+    for qi in range(doc.shape[0]):
+        assert len(set(doc[qi])) == 10                            # one hit per document
+    _check(store, score_oracle, q, corpus, 10, "prenormalized-angular", doc_of_row)
+    store.delete_doc(1)
+    dd = doc_of_row.copy()
+    dd[dd == 1] = -1
+    doc2, _, _ = store.search(q, 10)
+    assert 1 not in doc2[0]
+    _check(store, score_oracle, q, corpus, 10, "prenormalized-angular", dd)
+
+
+def test_empty_and_small(gpu_required):
+    from marqo_b200.engine import RowStore
+    store = RowStore(64)
+    doc, row, score = store.search(np.ones((2, 64), np.float32), 5)
+    assert (doc == -1).all() and (row == -1).all() and np.isneginf(score).all()
+    store.add(np.eye(3, 64, dtype=np.float32))
+    doc, row, score = store.search(np.eye(1, 64, dtype=np.float32), 5)
+    assert list(doc[0]) == [0, 1, 2, -1, -1]
+    assert score[0, 0] == 1.0                                    # identical vector => _score == 1.0
+    assert score[0, 1] == 0.5 and np.isneginf(score[0, 3])
+
+
+def test_growth_and_snapshot(gpu_required, score_oracle, tmp_path):
+    from marqo_b200.engine import RowStore
+    rng = np.random.default_rng(3)
+    d = 128
+    corpus = _unit_rows(rng, 2500, d)
+    store = RowStore(d, capacity=10)
+    for lo in range(0, 2500, 700):
+        store.add(corpus[lo:lo + 700])
+    q = _unit_rows(rng, 6, d)
+    _check(store, score_oracle, q, corpus, 10, "prenormalized-angular")
+    np.testing.assert_array_equal(store.get_row(17), corpus[17].astype(np.float16).astype(np.float32))
+    p = tmp_path / "snap.b200"
+    store.save(str(p))
+    again = RowStore.load(str(p))
+    assert len(again) == 2500 and again.dim == d
+    _check(again, score_oracle, q, corpus, 10, "prenormalized-angular")
+
+
+def test_argument_errors(gpu_required):
+    from marqo_b200.engine import RowStore
+    from marqo_b200._native import NativeError
+    with pytest.raises(NativeError):
+        RowStore(100)                                            # dim not a multiple of 64
+    store = RowStore(64)
+    with pytest.raises(ValueError):
+        store.add(np.zeros((2, 32), np.float32))
+    with pytest.raises(NativeError):
+        store.search(np.zeros((1, 64), np.float32), 0)
