@@ -193,6 +193,26 @@ int b200_model_last_timing(b200_model* m, float* ms, int* launches);
  * out = mean_i(w_i * v_i); if normalize and |out| > 0: out /= |out|.  fp64 arithmetic. */
 int b200_fuse_vectors(const double* vecs, const double* weights, int n, int dim, int normalize, double* out);
 
+/* ===================================================================================== */
+/* Diagnostics: run ONE kernel of the encoder on host data (used by the kernel-level     */
+/* numerics tests; not part of the reference-facing surface).                            */
+/* ===================================================================================== */
+
+/* out[M,N] = act(A[M,K] @ W[N,K]^T + bias) (+ residual); A and W are rounded to bf16 on the device, fp32
+ * accumulate; act: 0 none, 1 erf-GELU, 2 QuickGELU; bias/residual may be NULL; out_bf16 != 0 rounds the result to
+ * bf16 before it is returned as fp32. */
+int b200_debug_gemm(int device, const float* A, const float* W, const float* bias, const float* residual, int M, int N,
+                    int K, int act, int out_bf16, float* out);
+/* softmax(q k^T / 8 + mask) v over packed qkv fp32 [B*S, 3*W] (rounded to bf16); mask: 0 none, 1 causal,
+ * 2 key length (kv_len int32 [B]).  out fp32 [B*S, W]. */
+int b200_debug_attention(int device, const float* qkv, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+                         float* out);
+/* LayerNorm over rows of fp32 [rows, w]. */
+int b200_debug_layernorm(int device, const float* x, const float* gamma, const float* beta, float eps, int rows, int w,
+                         float* out);
+/* Pillow-compatible bicubic resize (shortest side -> S) + centre crop of uint8 HWC images [n,h,w,3] -> [n,S,S,3]. */
+int b200_debug_resize(int device, const uint8_t* hwc, int n, int h, int w, int S, uint8_t* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,153 @@
+// Diagnostic entry points: run one encoder kernel on host data (kernel-level numerics tests).
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+using namespace mb;
+
+namespace {
+
+struct Scratch {
+    std::vector<void*> ptrs;
+    cudaStream_t s = nullptr;
+    ~Scratch() {
+        for (void* p : ptrs) cudaFree(p);
+        if (s) cudaStreamDestroy(s);
+    }
+    template <class T>
+    T* alloc(size_t n) {
+        void* p = nullptr;
+        MB_CUDA(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
+        ptrs.push_back(p);
+        return reinterpret_cast<T*>(p);
+    }
+    template <class T>
+    T* upload(const T* h, size_t n) {
+        T* d = alloc<T>(n);
+        MB_CUDA(cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice));
+        return d;
+    }
+    __nv_bfloat16* upload_bf16(const float* h, size_t n) {
+        float* f = upload(h, n);
+        __nv_bfloat16* b = alloc<__nv_bfloat16>(n);
+        kernels::f32_to_bf16(f, b, (long long)n, s);
+        return b;
+    }
+};
+
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* src, float* dst, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+void require_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        fail(B200_ERR_NO_DEVICE, "CUDA device %d not available (marqo_b200 has no CPU fallback)", device);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_debug_gemm(int device, const float* A, const float* W, const float* bias, const float* residual, int M, int N,
+                    int K, int act, int out_bf16, float* out) {
+    return guarded([&] {
+        MB_CHECK_ARG(A && W && out, "NULL buffer");
+        MB_CHECK_ARG(M > 0 && N > 0 && K > 0, "M, N, K must be positive");
+        require_device(device);
+        DeviceGuard g(device);
+        Scratch sc;
+        MB_CUDA(cudaStreamCreate(&sc.s));
+        __nv_bfloat16* dA = sc.upload_bf16(A, (size_t)M * K);
+        __nv_bfloat16* dW = sc.upload_bf16(W, (size_t)N * K);
+        float* dOut = sc.alloc<float>((size_t)M * N);
+        gemm::Epilogue ep;
+        ep.bias = bias ? sc.upload(bias, (size_t)N) : nullptr;
+        ep.residual = residual ? sc.upload(residual, (size_t)M * N) : nullptr;
+        ep.ldr = N;
+        ep.act = act;
+        ep.ldo = N;
+        __nv_bfloat16* dOutB = nullptr;
+        if (out_bf16) {
+            dOutB = sc.alloc<__nv_bfloat16>((size_t)M * N);
+            ep.out = dOutB;
+            ep.out_fp32 = 0;
+        } else {
+            ep.out = dOut;
+            ep.out_fp32 = 1;
+        }
+        gemm::launch(dA, K, dW, M, N, K, ep, sm_count(device), sc.s);
+        if (out_bf16) {
+            const long long n = (long long)M * N;
+            bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sc.s>>>(dOutB, dOut, n);
+        }
+        MB_CUDA(cudaGetLastError());
+        MB_CUDA(cudaStreamSynchronize(sc.s));
+        MB_CUDA(cudaMemcpy(out, dOut, (size_t)M * N * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int b200_debug_attention(int device, const float* qkv, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+                         float* out) {
+    return guarded([&] {
+        MB_CHECK_ARG(qkv && out, "NULL buffer");
+        MB_CHECK_ARG(B > 0 && S > 0 && W > 0 && H > 0, "B, S, W, H must be positive");
+        require_device(device);
+        DeviceGuard g(device);
+        Scratch sc;
+        MB_CUDA(cudaStreamCreate(&sc.s));
+        const size_t M = (size_t)B * S;
+        __nv_bfloat16* dq = sc.upload_bf16(qkv, M * 3 * W);
+        __nv_bfloat16* dO = sc.alloc<__nv_bfloat16>(M * W);
+        float* dOut = sc.alloc<float>(M * W);
+        const int32_t* dlen = kv_len ? sc.upload(kv_len, (size_t)B) : nullptr;
+        attention::launch(dq, dO, B, S, W, H, mask, dlen, sc.s);
+        const long long n = (long long)M * W;
+        bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sc.s>>>(dO, dOut, n);
+        MB_CUDA(cudaGetLastError());
+        MB_CUDA(cudaStreamSynchronize(sc.s));
+        MB_CUDA(cudaMemcpy(out, dOut, M * W * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int b200_debug_layernorm(int device, const float* x, const float* gamma, const float* beta, float eps, int rows, int w,
+                         float* out) {
+    return guarded([&] {
+        MB_CHECK_ARG(x && gamma && beta && out, "NULL buffer");
+        require_device(device);
+        DeviceGuard g(device);
+        Scratch sc;
+        MB_CUDA(cudaStreamCreate(&sc.s));
+        float* dx = sc.upload(x, (size_t)rows * w);
+        float* dg = sc.upload(gamma, (size_t)w);
+        float* db = sc.upload(beta, (size_t)w);
+        float* dout = sc.alloc<float>((size_t)rows * w);
+        kernels::layernorm(dx, w, dg, db, eps, rows, w, dout, nullptr, sc.s);
+        MB_CUDA(cudaStreamSynchronize(sc.s));
+        MB_CUDA(cudaMemcpy(out, dout, (size_t)rows * w * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int b200_debug_resize(int device, const uint8_t* hwc, int n, int h, int w, int S, uint8_t* out) {
+    return guarded([&] {
+        MB_CHECK_ARG(hwc && out, "NULL buffer");
+        MB_CHECK_ARG(n > 0 && h > 0 && w > 0 && S > 0, "n, h, w, S must be positive");
+        require_device(device);
+        DeviceGuard g(device);
+        Scratch sc;
+        MB_CUDA(cudaStreamCreate(&sc.s));
+        uint8_t* din = sc.upload(hwc, (size_t)n * h * w * 3);
+        uint8_t* dout = sc.alloc<uint8_t>((size_t)n * S * S * 3);
+        kernels::resize_crop_u8(din, n, h, w, S, dout, sc.s);
+        MB_CUDA(cudaStreamSynchronize(sc.s));
+        MB_CUDA(cudaMemcpy(out, dout, (size_t)n * S * S * 3, cudaMemcpyDeviceToHost));
+    });
+}
+
+}  // extern "C"

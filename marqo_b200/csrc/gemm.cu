@@ -1,0 +1,286 @@
+#include "gemm.cuh"
+
+#include <mutex>
+
+#include "ptx.cuh"
+
+namespace mb {
+namespace gemm {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int ACC_STAGES = 2;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;
+constexpr int SMEM_LIMIT = 232448;
+
+template <int BN>
+struct Cfg {
+    static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
+    static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES > 8 ? 8 : (SMEM_LIMIT - 2048) / STAGE_BYTES;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN < 32 ? 32 : ACC_STAGES * BN;
+};
+
+struct Params {
+    int M, N, K;
+    int tiles_m, tiles_n;
+    Epilogue ep;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == ACT_GELU) return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    if (act == ACT_QUICKGELU) return x / (1.0f + __expf(-1.702f * x));
+    return x;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)C::STAGES * A_STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint64_t* empty = full + C::STAGES;
+    uint64_t* tfull = empty + C::STAGES;
+    uint64_t* tempty = tfull + ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int kblocks = p.K / BK;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_a);
+        ptx::prefetch_tmap(&tmap_b);
+        for (int i = 0; i < C::STAGES; ++i) {
+            ptx::mbar_init(&full[i], 1);
+            ptx::mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < ACC_STAGES; ++i) {
+            ptx::mbar_init(&tfull[i], 1);
+            ptx::mbar_init(&tempty[i], 4);
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int m0 = (t / p.tiles_n) * BM;
+                const int n0 = (t % p.tiles_n) * BN;
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                    ptx::tma_load_2d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, &full[stage], kb * BK, m0,
+                                     ptx::kEvictNormal);
+                    ptx::tma_load_2d(smem_b + (size_t)stage * C::B_STAGE_BYTES, &tmap_b, &full[stage], kb * BK, n0,
+                                     ptx::kEvictLast);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = ptx::make_idesc_f16(1 /*bf16*/, BM, BN);
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+            ptx::tc_fence_after();
+            for (int kb = 0; kb < kblocks; ++kb) {
+                ptx::mbar_wait(&full[stage], phase);
+                ptx::tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_base = ptx::smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES);
+                    const uint32_t b_base = ptx::smem_u32(smem_b + (size_t)stage * C::B_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        ptx::umma_f16(tmem_base + acc * BN, ptx::make_desc_k_sw128(a_base + k * UMMA_K * 2),
+                                      ptx::make_desc_k_sw128(b_base + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty[stage]);
+                    if (kb == kblocks - 1) ptx::umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++stage == C::STAGES) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            if (++acc == ACC_STAGES) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue (TMEM -> regs -> global)
+        const int sp = warp & 3;
+        const Epilogue& ep = p.ep;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int m0 = (t / p.tiles_n) * BM;
+            const int nt0 = (t % p.tiles_n) * BN;
+            const int row = m0 + sp * 32 + lane;
+            const bool row_ok = row < p.M;
+            long long orow = row;
+            int brow = 0;
+            if (ep.remap_group > 0) {
+                const int b = row / ep.remap_group, i = row - b * ep.remap_group;
+                orow = (long long)b * (ep.remap_group + 1) + 1 + i;
+                brow = 1 + i;
+            }
+            ptx::mbar_wait(&tfull[acc], acc_phase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(sp * 32) << 16) + acc * BN + c * 32, v);
+                ptx::tmem_ld_wait();
+                if (c == BN / 32 - 1) {
+                    // accumulator fully drained into registers: hand it back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+                }
+                const int n0 = nt0 + c * 32;
+                if (row_ok && n0 < p.N) {
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (ep.bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(b4 + j);
+                        f[4 * j] += b.x;
+                        f[4 * j + 1] += b.y;
+                        f[4 * j + 2] += b.z;
+                        f[4 * j + 3] += b.w;
+                    }
+                }
+                if (ep.act != ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
+                }
+                if (ep.rowbias) {
+                    const float4* r4 = reinterpret_cast<const float4*>(ep.rowbias + (size_t)brow * p.N + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = __ldg(r4 + j);
+                        f[4 * j] += b.x;
+                        f[4 * j + 1] += b.y;
+                        f[4 * j + 2] += b.z;
+                        f[4 * j + 3] += b.w;
+                    }
+                }
+                if (ep.residual) {
+                    const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = r4[j];
+                        f[4 * j] += b.x;
+                        f[4 * j + 1] += b.y;
+                        f[4 * j + 2] += b.z;
+                        f[4 * j + 3] += b.w;
+                    }
+                }
+                if (ep.out_fp32) {
+                    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)orow * ep.ldo + n0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                }
+                }
+            }
+            if (++acc == ACC_STAGES) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+void configure() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)Cfg<256>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)Cfg<128>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)Cfg<64>::SMEM_BYTES));
+    });
+}
+
+template <int BN>
+static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const Epilogue& ep,
+                      int sms, cudaStream_t stream) {
+    Params p;
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.tiles_m = (M + BM - 1) / BM;
+    p.tiles_n = (N + BN - 1) / BN;
+    p.ep = ep;
+    CUtensorMap ta = make_tmap_2d(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK,
+                                  BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap tb = make_tmap_2d(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, BK,
+                                  BN, CU_TENSOR_MAP_SWIZZLE_128B);
+    const int grid = std::min(p.tiles_m * p.tiles_n, sms);
+    gemm_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
+    MB_CUDA(cudaGetLastError());
+}
+
+void launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const Epilogue& ep, int sms,
+            cudaStream_t stream) {
+    if (M <= 0 || N <= 0) return;
+    if (K <= 0 || K % BK != 0) fail(B200_ERR_INTERNAL, "gemm: K = %d must be a positive multiple of %d", K, BK);
+    if (N % 32 != 0) fail(B200_ERR_INTERNAL, "gemm: N = %d must be a multiple of 32", N);
+    if (lda % 8 != 0 || ep.ldo % 8 != 0) fail(B200_ERR_INTERNAL, "gemm: leading dimensions must be multiples of 8");
+    configure();
+    // Largest tile that wastes no columns, otherwise the widest one.
+    if (N % 256 == 0 || N > 512)
+        launch_bn<256>(A, lda, W, M, N, K, ep, sms, stream);
+    else if (N % 128 == 0 || N > 128)
+        launch_bn<128>(A, lda, W, M, N, K, ep, sms, stream);
+    else
+        launch_bn<64>(A, lda, W, M, N, K, ep, sms, stream);
+}
+
+}  // namespace gemm
+}  // namespace mb

@@ -139,3 +139,170 @@ def topk_merge(doc: np.ndarray, row: np.ndarray, score: np.ndarray) -> Tuple[np.
     osc = np.empty((nq, k), np.float64)
     N.check(N.load().b200_topk_merge(ns, nq, k, _ptr(doc), _ptr(row), _ptr(score), _ptr(od), _ptr(orow), _ptr(osc)))
     return od, orow, osc
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Encoders (b200_model_*)
+# ---------------------------------------------------------------------------------------------------------
+def _to_numpy_f32(t) -> np.ndarray:
+    if hasattr(t, "detach"):
+        t = t.detach().to("cpu").float().numpy()
+    return np.ascontiguousarray(t, dtype=np.float32)
+
+
+class Encoder:
+    """A CLIP (vision + text towers) or BERT encoder resident on one GPU.
+
+    `config` keys — CLIP: embed_dim, act ("gelu"|"quickgelu"), mean, std, vision{width,layers,heads,mlp,patch,
+    image_size}, text{width,layers,heads,mlp,ctx,vocab};  BERT: width, layers, heads, mlp, vocab, max_pos, type_vocab,
+    pool ("mean"|"cls").  `weights` maps checkpoint parameter names (open_clip state_dict names / HF BertModel names) to
+    fp32 arrays or torch tensors.
+    """
+
+    def __init__(self, arch: str, config: dict, weights: dict, device: int = 0, max_batch: int = 256):
+        self._lib = N.load()
+        self.arch = arch
+        self.device = int(device)
+        d = N.ModelDesc()
+        d.max_batch = int(max_batch)
+        if arch == "clip":
+            d.arch = N.ARCH_CLIP
+            d.embed_dim = int(config["embed_dim"])
+            d.act = N.ACT_QUICKGELU if config.get("act", "gelu") == "quickgelu" else N.ACT_GELU
+            mean = config.get("mean", (0.48145466, 0.4578275, 0.40821073))
+            std = config.get("std", (0.26862954, 0.26130258, 0.27577711))
+            for i in range(3):
+                d.image_mean[i] = float(np.float32(mean[i]))
+                d.image_std[i] = float(np.float32(std[i]))
+            v, t = config.get("vision"), config.get("text")
+            if v:
+                d.vision = N.TowerDesc(v["width"], v["layers"], v["heads"], v["mlp"], 0, 0, v.get("image_size", 224),
+                                       v["patch"])
+            if t:
+                d.text = N.TowerDesc(t["width"], t["layers"], t["heads"], t["mlp"], t["ctx"], t["vocab"], 0, 0)
+            self.image_size = v.get("image_size", 224) if v else 0
+        elif arch == "bert":
+            d.arch = N.ARCH_BERT
+            d.embed_dim = int(config["width"])
+            d.pool = N.POOL_CLS if config.get("pool", "mean") == "cls" else N.POOL_MEAN
+            d.type_vocab = int(config.get("type_vocab", 2))
+            d.text = N.TowerDesc(config["width"], config["layers"], config["heads"], config["mlp"],
+                                 config.get("max_pos", 512), config["vocab"], 0, 0)
+            self.image_size = 0
+        else:
+            raise ValueError(f"unknown arch {arch!r}")
+        self.embed_dim = int(d.embed_dim)
+        h = C.c_void_p()
+        N.check(self._lib.b200_model_create(self.device, C.byref(d), C.byref(h)))
+        self._h = h
+        try:
+            for name, t in weights.items():
+                a = _to_numpy_f32(t)
+                N.check(self._lib.b200_model_load_tensor(h, name.encode(), _ptr(a), a.size))
+            N.check(self._lib.b200_model_finalize(h))
+        except Exception:
+            self.close()
+            raise
+
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.b200_model_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _handle(self):
+        if not self._h:
+            raise RuntimeError("Encoder is closed")
+        return self._h
+
+    def encode_images_u8(self, hwc: np.ndarray, normalize: bool = True) -> np.ndarray:
+        a = _as(hwc, np.uint8)
+        if a.ndim != 4 or a.shape[3] != 3:
+            raise ValueError(f"expected uint8 [n, H, W, 3], got {a.shape}")
+        out = np.empty((a.shape[0], self.embed_dim), np.float32)
+        N.check(self._lib.b200_model_encode_images_u8(self._handle(), _ptr(a), a.shape[0], a.shape[1], a.shape[2],
+                                                      1 if normalize else 0, _ptr(out)))
+        return out
+
+    def encode_images_f32(self, chw, normalize: bool = True) -> np.ndarray:
+        a = _to_numpy_f32(chw)
+        if a.ndim != 4 or a.shape[1] != 3 or a.shape[2] != self.image_size or a.shape[3] != self.image_size:
+            raise ValueError(f"expected fp32 [n, 3, {self.image_size}, {self.image_size}], got {a.shape}")
+        out = np.empty((a.shape[0], self.embed_dim), np.float32)
+        N.check(self._lib.b200_model_encode_images_f32(self._handle(), _ptr(a), a.shape[0], 1 if normalize else 0,
+                                                       _ptr(out)))
+        return out
+
+    def encode_tokens(self, ids, attn_mask=None, normalize: bool = True) -> np.ndarray:
+        i = _as(ids.cpu().numpy() if hasattr(ids, "cpu") else ids, np.int32)
+        if i.ndim != 2:
+            raise ValueError(f"expected int [n, seq] token ids, got {i.shape}")
+        mk = None
+        if attn_mask is not None:
+            mk = _as(attn_mask.cpu().numpy() if hasattr(attn_mask, "cpu") else attn_mask, np.int32)
+            if mk.shape != i.shape:
+                raise ValueError("attention mask shape must match ids")
+        out = np.empty((i.shape[0], self.embed_dim), np.float32)
+        N.check(self._lib.b200_model_encode_tokens(self._handle(), _ptr(i), _ptr(mk), i.shape[0], i.shape[1],
+                                                   1 if normalize else 0, _ptr(out)))
+        return out
+
+    def encode_images_u8_device(self, d_ptr: int, n: int, h: int, w: int, d_out_ptr: int, normalize: bool = True,
+                                sync: bool = True) -> None:
+        N.check(self._lib.b200_model_encode_images_u8_device(self._handle(), C.c_void_p(d_ptr), n, h, w,
+                                                             1 if normalize else 0, C.c_void_p(d_out_ptr),
+                                                             1 if sync else 0))
+
+    def encode_tokens_device(self, d_ids_ptr: int, d_mask_ptr: Optional[int], n: int, seq: int, d_out_ptr: int,
+                             normalize: bool = True, sync: bool = True) -> None:
+        N.check(self._lib.b200_model_encode_tokens_device(self._handle(), C.c_void_p(d_ids_ptr),
+                                                          C.c_void_p(d_mask_ptr) if d_mask_ptr else None, n, seq,
+                                                          1 if normalize else 0, C.c_void_p(d_out_ptr),
+                                                          1 if sync else 0))
+
+    def last_timing(self) -> Tuple[float, int]:
+        ms, n = C.c_float(0), C.c_int(0)
+        N.check(self._lib.b200_model_last_timing(self._handle(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Kernel-level diagnostics (b200_debug_*)
+# ---------------------------------------------------------------------------------------------------------
+def debug_gemm(A, W, bias=None, residual=None, act: int = 0, out_bf16: bool = False, device: int = 0) -> np.ndarray:
+    A, W = _as(A, np.float32), _as(W, np.float32)
+    M, K = A.shape
+    Nn = W.shape[0]
+    b = None if bias is None else _as(bias, np.float32)
+    r = None if residual is None else _as(residual, np.float32)
+    out = np.empty((M, Nn), np.float32)
+    N.check(N.load().b200_debug_gemm(device, _ptr(A), _ptr(W), _ptr(b), _ptr(r), M, Nn, K, act, 1 if out_bf16 else 0,
+                                     _ptr(out)))
+    return out
+
+
+def debug_attention(qkv, B: int, S: int, W: int, H: int, mask: int = 0, kv_len=None, device: int = 0) -> np.ndarray:
+    q = _as(qkv, np.float32)
+    kl = None if kv_len is None else _as(kv_len, np.int32)
+    out = np.empty((B * S, W), np.float32)
+    N.check(N.load().b200_debug_attention(device, _ptr(q), B, S, W, H, mask, _ptr(kl), _ptr(out)))
+    return out
+
+
+def debug_layernorm(x, gamma, beta, eps: float, device: int = 0) -> np.ndarray:
+    x, g, b = _as(x, np.float32), _as(gamma, np.float32), _as(beta, np.float32)
+    out = np.empty_like(x)
+    N.check(N.load().b200_debug_layernorm(device, _ptr(x), _ptr(g), _ptr(b), eps, x.shape[0], x.shape[1], _ptr(out)))
+    return out
+
+
+def debug_resize(hwc, S: int, device: int = 0) -> np.ndarray:
+    a = _as(hwc, np.uint8)
+    out = np.empty((a.shape[0], S, S, 3), np.uint8)
+    N.check(N.load().b200_debug_resize(device, _ptr(a), a.shape[0], a.shape[1], a.shape[2], S, _ptr(out)))
+    return out

@@ -1,0 +1,126 @@
+"""GPU parity of the encoders through the C ABI vs the CPU fp32 oracle (oracle/encoders.py) on the
+same seeded weights and inputs.  Bar (BASELINE.json north_star): cosine >= 1 - 1e-3 per vector."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoders as E
+
+pytestmark = pytest.mark.gpu
+COS_TOL = 1e-3
+
+
+def _cos(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return torch.nn.functional.cosine_similarity(a, b, dim=-1)
+
+
+def _clip_config(cfg: E.ClipCfg) -> dict:
+    def tower(t):
+        return dict(width=t.width, layers=t.layers, heads=t.heads, mlp=t.mlp, ctx=t.ctx, vocab=t.vocab,
+                    image_size=t.image_size, patch=t.patch)
+    return dict(embed_dim=cfg.embed_dim, act=cfg.act, mean=cfg.mean, std=cfg.std, vision=tower(cfg.vision),
+                text=tower(cfg.text))
+
+
+def _bert_config(cfg: E.BertCfg) -> dict:
+    return dict(width=cfg.width, layers=cfg.layers, heads=cfg.heads, mlp=cfg.mlp, vocab=cfg.vocab, max_pos=cfg.max_pos,
+                type_vocab=cfg.type_vocab, pool=cfg.pool)
+
+
+def _text_ids(g, n, ctx, vocab):
+    ids = torch.zeros(n, ctx, dtype=torch.int64)
+    for b in range(n):
+        L = int(torch.randint(3, ctx + 1, (1,), generator=g))
+        ids[b, 0] = vocab - 2
+        ids[b, 1:L - 1] = torch.randint(1, vocab - 2, (L - 2,), generator=g)
+        ids[b, L - 1] = vocab - 1
+    return ids
+
+
+def _check(got, ref, norm=True):
+    got = torch.from_numpy(got)
+    assert torch.isfinite(got).all()
+    c = _cos(got, ref)
+    assert float((1 - c).max()) < COS_TOL, f"min cosine {float(c.min())}"
+    if norm:
+        assert torch.allclose(got.norm(dim=-1), torch.ones(got.shape[0]), atol=1e-5)
+
+
+@pytest.mark.parametrize("act", ["gelu", "quickgelu"])
+def test_tiny_clip(gpu_required, act):
+    from marqo_b200.engine import Encoder
+    cfg = E.tiny_clip(act)
+    sd = E.make_clip_weights(cfg, seed=11)
+    enc = Encoder("clip", _clip_config(cfg), sd, max_batch=8)
+    g = torch.Generator().manual_seed(0)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(5, 224, 224, 3), dtype=np.uint8)
+    px = E.clip_preprocess_u8(img)
+    _check(enc.encode_images_u8(img), E.clip_encode_image(sd, cfg, px))
+    _check(enc.encode_images_f32(px), E.clip_encode_image(sd, cfg, px))
+    un = torch.from_numpy(enc.encode_images_u8(img, normalize=False))
+    ref_un = E.clip_encode_image(sd, cfg, px, normalize=False)
+    assert float((1 - _cos(un, ref_un)).max()) < COS_TOL
+    assert torch.allclose(un.norm(dim=-1), ref_un.norm(dim=-1), rtol=2e-2)
+    ids = _text_ids(g, 11, cfg.text.ctx, cfg.text.vocab)            # 11 > max_batch: exercises sub-batching
+    _check(enc.encode_tokens(ids.numpy()), E.clip_encode_text(sd, cfg, ids))
+    # non-square input goes through the resize kernel; oracle goes through PIL
+    big = rng.integers(0, 256, size=(2, 300, 400, 3), dtype=np.uint8)
+    _check(enc.encode_images_u8(big), E.clip_encode_image(sd, cfg, E.clip_preprocess_u8(big)))
+
+
+@pytest.mark.parametrize("pool", ["mean", "cls"])
+def test_tiny_bert(gpu_required, pool):
+    from marqo_b200.engine import Encoder
+    cfg = E.tiny_bert(pool)
+    sd = E.make_bert_weights(cfg, seed=12)
+    enc = Encoder("bert", _bert_config(cfg), sd, max_batch=16)
+    g = torch.Generator().manual_seed(1)
+    ids = torch.randint(1, cfg.vocab, (6, 40), generator=g)
+    mask = torch.ones(6, 40, dtype=torch.int64)
+    for b, L in enumerate([40, 3, 17, 1, 33, 40]):
+        mask[b, L:] = 0
+        ids[b, L:] = 0
+    _check(enc.encode_tokens(ids.numpy(), mask.numpy()), E.bert_encode(sd, cfg, ids, mask))
+    _check(enc.encode_tokens(ids.numpy()), E.bert_encode(sd, cfg, ids, None))
+
+
+def test_vit_b_32(gpu_required):
+    """BASELINE.json configs[1] architecture (open_clip/ViT-B-32), seeded weights, batch 8."""
+    from marqo_b200.engine import Encoder
+    cfg = E.CLIP_VIT_B_32
+    sd = E.make_clip_weights(cfg, seed=1234)
+    enc = Encoder("clip", _clip_config(cfg), sd, max_batch=8)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, size=(8, 224, 224, 3), dtype=np.uint8)
+    _check(enc.encode_images_u8(img), E.clip_encode_image(sd, cfg, E.clip_preprocess_u8(img)))
+    ids = _text_ids(torch.Generator().manual_seed(2), 8, 77, cfg.text.vocab)
+    _check(enc.encode_tokens(ids.numpy()), E.clip_encode_text(sd, cfg, ids))
+
+
+def test_e5_base_cfg1(gpu_required):
+    """BASELINE.json configs[0]: hf/e5-base-v2 architecture, batch 8, 128 tokens (+ a ragged variant)."""
+    from marqo_b200.engine import Encoder
+    cfg = E.E5_BASE
+    sd = E.make_bert_weights(cfg, seed=1234)
+    enc = Encoder("bert", _bert_config(cfg), sd, max_batch=8)
+    g = torch.Generator().manual_seed(0)
+    ids = torch.cat([torch.full((8, 1), 101), torch.randint(1000, 30000, (8, 126), generator=g), torch.full((8, 1), 102)], 1)
+    _check(enc.encode_tokens(ids.numpy()), E.bert_encode(sd, cfg, ids))
+    mask = torch.ones(8, 128, dtype=torch.int64)
+    for b, L in enumerate([16, 32, 48, 64, 80, 96, 112, 128]):
+        mask[b, L:] = 0
+        ids[b, L:] = 0
+    _check(enc.encode_tokens(ids.numpy(), mask.numpy()), E.bert_encode(sd, cfg, ids, mask))
+
+
+def test_missing_weight_is_an_error(gpu_required):
+    from marqo_b200.engine import Encoder
+    from marqo_b200._native import NativeError, ERR_MISSING_WEIGHT
+    cfg = E.tiny_bert()
+    sd = E.make_bert_weights(cfg, seed=1)
+    del sd["encoder.layer.1.output.dense.bias"]
+    with pytest.raises(NativeError) as ei:
+        Encoder("bert", _bert_config(cfg), sd)
+    assert ei.value.code == ERR_MISSING_WEIGHT
