@@ -75,9 +75,15 @@ struct b200_model {
     size_t in_dev_bytes = 0;
     uint8_t* resized = nullptr;       // [max_batch, S, S, 3]
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;  // created by the handle; `stream` may be replaced by a caller's stream
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing_valid = false;
     int last_launches = 0;
+    // optional per-kernel-class device timing (bench.py's roofline numerator)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_ev;  // pairs
+    std::vector<int> prof_cls;         // 0 = gemm, 1 = attention
+    int prof_n = 0;
     std::mutex mu;
 };
 
@@ -109,7 +115,8 @@ void model_free(b200_model* m) {
     cudaFree(m->resized);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
-    if (m->stream) cudaStreamDestroy(m->stream);
+    for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
     delete m;
 }
 
@@ -210,10 +217,39 @@ struct Counter {
     int n = 0;
 };
 
+struct ProfScope {
+    b200_model* m;
+    bool on;
+    ProfScope(b200_model* mm, int cls) : m(mm), on(mm->profiling) {
+        if (!on) return;
+        if ((size_t)(2 * m->prof_n + 2) > m->prof_ev.size()) {
+            for (int i = 0; i < 64; ++i) {
+                cudaEvent_t e;
+                MB_CUDA(cudaEventCreate(&e));
+                m->prof_ev.push_back(e);
+            }
+            m->prof_cls.resize(m->prof_ev.size() / 2);
+        }
+        m->prof_cls[m->prof_n] = cls;
+        MB_CUDA(cudaEventRecord(m->prof_ev[2 * m->prof_n], m->stream));
+    }
+    ~ProfScope() {
+        if (!on) return;
+        cudaEventRecord(m->prof_ev[2 * m->prof_n + 1], m->stream);
+        ++m->prof_n;
+    }
+};
+
 void linear(b200_model* m, Counter& c, const __nv_bfloat16* A, int M, int K, const __nv_bfloat16* W, int N,
             const gemm::Epilogue& ep) {
+    ProfScope ps(m, 0);
     gemm::launch(A, K, W, M, N, K, ep, m->sms, m->stream);
     ++c.n;
+}
+
+void attend(b200_model* m, int B, int S, int w, int heads, int mask_mode, const int32_t* kv_len) {
+    ProfScope ps(m, 1);
+    attention::launch(m->qkv, m->o, B, S, w, heads, mask_mode, kv_len, m->stream);
 }
 
 // Pre-LN residual blocks (open_clip ResidualAttentionBlock).
@@ -227,7 +263,7 @@ void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, i
         e1.out = m->qkv;
         e1.ldo = 3 * w;
         linear(m, c, m->h, M, w, L.w_qkv, 3 * w, e1);
-        attention::launch(m->qkv, m->o, B, S, w, T.d.heads, mask_mode, nullptr, m->stream);
+        attend(m, B, S, w, T.d.heads, mask_mode, nullptr);
         gemm::Epilogue e2;
         e2.bias = L.b_o;
         e2.residual = m->x;
@@ -265,7 +301,7 @@ void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
         e1.out = m->qkv;
         e1.ldo = 3 * w;
         linear(m, c, m->h, M, w, L.w_qkv, 3 * w, e1);
-        attention::launch(m->qkv, m->o, B, S, w, T.d.heads, attention::MASK_KEYLEN, m->aux, m->stream);
+        attend(m, B, S, w, T.d.heads, attention::MASK_KEYLEN, m->aux);
         gemm::Epilogue e2;
         e2.bias = L.b_o;
         e2.residual = m->x;
@@ -443,7 +479,8 @@ int b200_model_create(int device, const b200_model_desc* desc, b200_model** out)
             m->device = device;
             m->desc = *desc;
             m->sms = sm_count(device);
-            MB_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+            MB_CUDA(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+            m->stream = m->own_stream;
             MB_CUDA(cudaEventCreate(&m->ev0));
             MB_CUDA(cudaEventCreate(&m->ev1));
             m->vision.present = has_vision;
@@ -682,6 +719,46 @@ int b200_model_encode_tokens_device(b200_model* m, const int32_t* d_ids, const i
         encode_tokens_dev(m, tr.c, d_ids, d_attn_mask, n, seq, normalize, d_out);
         tr.finish();
         if (sync) MB_CUDA(cudaStreamSynchronize(m->stream));
+    });
+}
+
+int b200_model_set_stream(b200_model* m, void* cuda_stream) {
+    return guarded([&] {
+        MB_CHECK_ARG(m != nullptr, "model is NULL");
+        std::lock_guard<std::mutex> lk(m->mu);
+        DeviceGuard g(m->device);
+        MB_CUDA(cudaStreamSynchronize(m->stream));
+        m->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : m->own_stream;
+    });
+}
+
+int b200_model_set_profiling(b200_model* m, int enable) {
+    return guarded([&] {
+        MB_CHECK_ARG(m != nullptr, "model is NULL");
+        std::lock_guard<std::mutex> lk(m->mu);
+        m->profiling = enable != 0;
+        m->prof_n = 0;
+    });
+}
+
+int b200_model_profile(b200_model* m, float* gemm_ms, int* gemm_launches, float* attention_ms, int* attention_launches) {
+    return guarded([&] {
+        MB_CHECK_ARG(m && gemm_ms && gemm_launches && attention_ms && attention_launches, "NULL argument");
+        std::lock_guard<std::mutex> lk(m->mu);
+        DeviceGuard g(m->device);
+        float ms[2] = {0.f, 0.f};
+        int cnt[2] = {0, 0};
+        for (int i = 0; i < m->prof_n; ++i) {
+            MB_CUDA(cudaEventSynchronize(m->prof_ev[2 * i + 1]));
+            float t = 0.f;
+            MB_CUDA(cudaEventElapsedTime(&t, m->prof_ev[2 * i], m->prof_ev[2 * i + 1]));
+            ms[m->prof_cls[i]] += t;
+            ++cnt[m->prof_cls[i]];
+        }
+        *gemm_ms = ms[0];
+        *gemm_launches = cnt[0];
+        *attention_ms = ms[1];
+        *attention_launches = cnt[1];
     });
 }
 

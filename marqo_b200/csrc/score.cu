@@ -531,6 +531,7 @@ struct b200_index {
     int32_t* o_row = nullptr;
     double* o_score = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool timing_valid = false;
     std::mutex mu;
@@ -553,7 +554,7 @@ void index_free(b200_index* ix) {
     cudaFree(ix->o_score);
     for (auto& e : ix->ev)
         if (e) cudaEventDestroy(e);
-    if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     delete ix;
 }
 
@@ -610,7 +611,8 @@ b200_index* index_new(int device, int dim, int metric, int64_t capacity_rows) {
         ix->dim = dim;
         ix->metric = metric;
         ix->sms = sm_count(device);
-        MB_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+        MB_CUDA(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
+        ix->stream = ix->own_stream;
         for (auto& e : ix->ev) MB_CUDA(cudaEventCreate(&e));
         cuda_alloc((void**)&ix->qh, (size_t)MQ * dim * sizeof(__half));
         cuda_alloc((void**)&ix->q_stage, (size_t)MQ * dim * sizeof(float));
@@ -883,6 +885,16 @@ int b200_index_search_device(b200_index* ix, const float* d_q, int nq, int k, in
         DeviceGuard g(ix->device);
         search_device(ix, d_q, nq, k, d_out_doc, d_out_row, d_out_score);
         if (sync) MB_CUDA(cudaStreamSynchronize(ix->stream));
+    });
+}
+
+int b200_index_set_stream(b200_index* ix, void* cuda_stream) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix != nullptr, "index is NULL");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        MB_CUDA(cudaStreamSynchronize(ix->stream));
+        ix->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ix->own_stream;
     });
 }
 

@@ -110,6 +110,9 @@ class RowStore:
                                                    C.c_void_p(d_doc_ptr), C.c_void_p(d_row_ptr),
                                                    C.c_void_p(d_score_ptr), 1 if sync else 0))
 
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        N.check(self._lib.b200_index_set_stream(self._handle(), C.c_void_p(cuda_stream) if cuda_stream else None))
+
     def last_timing(self) -> Tuple[float, float]:
         a, b = C.c_float(0), C.c_float(0)
         N.check(self._lib.b200_index_last_timing(self._handle(), C.byref(a), C.byref(b)))
@@ -264,6 +267,17 @@ class Encoder:
                                                           C.c_void_p(d_mask_ptr) if d_mask_ptr else None, n, seq,
                                                           1 if normalize else 0, C.c_void_p(d_out_ptr),
                                                           1 if sync else 0))
+
+    def set_stream(self, cuda_stream: Optional[int]) -> None:
+        N.check(self._lib.b200_model_set_stream(self._handle(), C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def set_profiling(self, on: bool) -> None:
+        N.check(self._lib.b200_model_set_profiling(self._handle(), 1 if on else 0))
+
+    def profile(self) -> dict:
+        g, gn, a, an = C.c_float(0), C.c_int(0), C.c_float(0), C.c_int(0)
+        N.check(self._lib.b200_model_profile(self._handle(), C.byref(g), C.byref(gn), C.byref(a), C.byref(an)))
+        return {"gemm_ms": g.value, "gemm_launches": gn.value, "attention_ms": a.value, "attention_launches": an.value}
 
     def last_timing(self) -> Tuple[float, int]:
         ms, n = C.c_float(0), C.c_int(0)
