@@ -145,7 +145,7 @@ def run_reference(args, rank: int, world: int):
         return
     import torch
     torch.set_num_threads(os.cpu_count() or 1)
-    sample = 8
+    sample = 4
     sd, cfg = make_oracle_model()
     rng = np.random.default_rng(0)
     img = rng.integers(0, 256, size=(sample, IMG, IMG, 3), dtype=np.uint8)
@@ -230,7 +230,8 @@ def main():
     sd = Wt.random_clip_weights(arch, 1234)
     enc = Encoder("clip", arch, sd, device=local_rank, max_batch=BATCH)
     del sd
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)      # the engine and the timing events share this stream
+    torch.cuda.set_stream(stream)
     enc.set_stream(stream.cuda_stream)
     E = enc.embed_dim
     g = torch.Generator(device=dev).manual_seed(rank)
@@ -363,7 +364,7 @@ def main():
     cpu = None
     if rank == 0 and not args.skip_cpu_baseline:
         torch.set_num_threads(os.cpu_count() or 1)
-        sample = 16
+        sample = 8
         sd_o, cfg_o = make_oracle_model()
         pix = img_host_np[:sample]
         oracle_embed_step(sd_o, cfg_o, pix[:2])

@@ -104,9 +104,9 @@ int b200_index_search(b200_index* ix, const float* q, int nq, int k, int32_t* ou
  * stream unless sync != 0. */
 int b200_index_search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_out_doc,
                              int32_t* d_out_row, double* d_out_score, int sync);
-/* Run this handle's work on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) instead of
- * the handle's own; NULL restores the private stream. */
-int b200_index_set_stream(b200_index* ix, void* cuda_stream);
+/* use_external != 0: run this handle's work on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
+ * stream; the value 0 is the legacy default stream).  use_external == 0 restores the handle's private stream. */
+int b200_index_set_stream(b200_index* ix, void* cuda_stream, int use_external);
 /* Device time (ms, CUDA events on the handle's stream) of the scan / merge kernels of the last
  * search call; used by bench.py for the roofline numerator. */
 int b200_index_last_timing(b200_index* ix, float* scan_ms, float* merge_ms);
@@ -187,7 +187,7 @@ int b200_model_encode_images_u8_device(b200_model* m, const uint8_t* d_hwc, int 
                                        float* d_out, int sync);
 int b200_model_encode_tokens_device(b200_model* m, const int32_t* d_ids, const int32_t* d_attn_mask, int n,
                                     int seq, int normalize, float* d_out, int sync);
-int b200_model_set_stream(b200_model* m, void* cuda_stream);
+int b200_model_set_stream(b200_model* m, void* cuda_stream, int use_external);
 /* Optional per-kernel-class device timing: when enabled every GEMM / attention launch of an encode call is
  * bracketed by CUDA events on the handle's stream; b200_model_profile returns their sums over every encode call
  * since profiling was last (re-)enabled. */

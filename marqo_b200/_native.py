@@ -58,7 +58,7 @@ _SIGNATURES = {
     "b200_index_get_row": (C.c_int, [_P, C.c_int64, _P]),
     "b200_index_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "b200_index_search_device": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int]),
-    "b200_index_set_stream": (C.c_int, [_P, _P]),
+    "b200_index_set_stream": (C.c_int, [_P, _P, C.c_int]),
     "b200_index_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "b200_topk_merge": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "b200_index_save": (C.c_int, [_P, C.c_char_p]),
@@ -72,7 +72,7 @@ _SIGNATURES = {
     "b200_model_encode_tokens": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P]),
     "b200_model_encode_images_u8_device": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
     "b200_model_encode_tokens_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int]),
-    "b200_model_set_stream": (C.c_int, [_P, _P]),
+    "b200_model_set_stream": (C.c_int, [_P, _P, C.c_int]),
     "b200_model_set_profiling": (C.c_int, [_P, C.c_int]),
     "b200_model_profile": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "b200_model_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int)]),

@@ -722,13 +722,13 @@ int b200_model_encode_tokens_device(b200_model* m, const int32_t* d_ids, const i
     });
 }
 
-int b200_model_set_stream(b200_model* m, void* cuda_stream) {
+int b200_model_set_stream(b200_model* m, void* cuda_stream, int use_external) {
     return guarded([&] {
         MB_CHECK_ARG(m != nullptr, "model is NULL");
         std::lock_guard<std::mutex> lk(m->mu);
         DeviceGuard g(m->device);
         MB_CUDA(cudaStreamSynchronize(m->stream));
-        m->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : m->own_stream;
+        m->stream = use_external ? reinterpret_cast<cudaStream_t>(cuda_stream) : m->own_stream;
     });
 }
 

@@ -348,74 +348,111 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeParams p) {
     int32_t* s_doc = s_row + p.sort_n;
     __shared__ int sel_row[KP], sel_doc[KP], sel_n;
     __shared__ double sel_dot[KP];
+    __shared__ float s_head[256];
+    __shared__ float s_thr;
+    __shared__ int s_count, s_valid;
 
     const int q = blockIdx.x;
     const int total = p.num_lists * KP;
-    for (int i = threadIdx.x; i < p.sort_n; i += blockDim.x) {
-        float s = -INFINITY;
-        int r = INT_MAX, d = -1;
-        if (i < total) {
+    // Every list is sorted, so the KP-th largest list HEAD is a lower bound of the global KP-th best score:
+    // only candidates >= that bound can be in the global top-KP.  This shrinks the sort from ~2.4k to ~KP..100 keys.
+    for (int l = threadIdx.x; l < p.num_lists; l += blockDim.x) {
+        const size_t src = ((size_t)l * MQ + q) * KP;
+        s_head[l] = p.in_row[src] >= 0 ? p.in_score[src] : -INFINITY;
+    }
+    if (threadIdx.x == 0) s_thr = -INFINITY;
+    __syncthreads();
+    if (p.num_lists >= KP) {
+        for (int l = threadIdx.x; l < p.num_lists; l += blockDim.x) {
+            const float h = s_head[l];
+            int rank = 0;
+            for (int j = 0; j < p.num_lists; ++j) rank += (s_head[j] > h) || (s_head[j] == h && j < l);
+            if (rank == KP - 1) s_thr = h;
+        }
+    }
+    __syncthreads();
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const float thr = attempt == 0 ? s_thr : -INFINITY;
+        if (threadIdx.x == 0) {
+            s_count = 0;
+            s_valid = 0;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int list = i / KP, e = i % KP;
             const size_t src = ((size_t)list * MQ + q) * KP + e;
             const int rr = p.in_row[src];
-            if (rr >= 0) {
-                s = p.in_score[src];
-                r = rr;
-                d = p.in_doc[src];
+            if (rr < 0) continue;
+            atomicAdd(&s_valid, 1);
+            const float sc = p.in_score[src];
+            if (sc >= thr) {
+                const int slot = atomicAdd(&s_count, 1);
+                s_score[slot] = sc;
+                s_row[slot] = rr;
+                s_doc[slot] = p.in_doc[src];
             }
         }
-        s_score[i] = s;
-        s_row[i] = r;
-        s_doc[i] = d;
-    }
-    __syncthreads();
-    // bitonic sort, order: (score desc, row asc)
-    for (int size = 2; size <= p.sort_n; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = threadIdx.x; i < p.sort_n / 2; i += blockDim.x) {
-                const int lo = 2 * i - (i & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = (lo & size) == 0;
-                const float sa = s_score[lo], sb = s_score[hi];
-                const int ra = s_row[lo], rb = s_row[hi];
-                const bool wrong = up ? approx_before(sb, rb, sa, ra) : approx_before(sa, ra, sb, rb);
-                if (wrong) {
-                    s_score[lo] = sb;
-                    s_score[hi] = sa;
-                    s_row[lo] = rb;
-                    s_row[hi] = ra;
-                    const int da = s_doc[lo];
-                    s_doc[lo] = s_doc[hi];
-                    s_doc[hi] = da;
+        __syncthreads();
+        const int count = s_count;
+        int n2 = 32;
+        while (n2 < count) n2 <<= 1;
+        for (int i = count + threadIdx.x; i < n2; i += blockDim.x) {
+            s_score[i] = -INFINITY;
+            s_row[i] = INT_MAX;
+            s_doc[i] = -1;
+        }
+        __syncthreads();
+        // bitonic sort, order: (score desc, row asc) — a total order, so the result does not depend on slot order
+        for (int size = 2; size <= n2; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = threadIdx.x; i < n2 / 2; i += blockDim.x) {
+                    const int lo = 2 * i - (i & (stride - 1));
+                    const int hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const float sa = s_score[lo], sb = s_score[hi];
+                    const int ra = s_row[lo], rb = s_row[hi];
+                    const bool wrong = up ? approx_before(sb, rb, sa, ra) : approx_before(sa, ra, sb, rb);
+                    if (wrong) {
+                        s_score[lo] = sb;
+                        s_score[hi] = sa;
+                        s_row[lo] = rb;
+                        s_row[hi] = ra;
+                        const int da = s_doc[lo];
+                        s_doc[lo] = s_doc[hi];
+                        s_doc[hi] = da;
+                    }
                 }
+                __syncthreads();
             }
-            __syncthreads();
         }
-    }
-    if (threadIdx.x == 0) {
-        int n = 0;
-        for (int i = 0; i < total && n < KP; ++i) {
-            if (s_row[i] == INT_MAX) break;
-            const int d = s_doc[i];
-            bool dup = false;
-            for (int j = 0; j < n; ++j) dup |= (sel_doc[j] == d);
-            if (dup) continue;
-            sel_row[n] = s_row[i];
-            sel_doc[n] = d;
-            if (p.cand_score) {
-                p.cand_score[(size_t)q * KP + n] = s_score[i];
-                p.cand_row[(size_t)q * KP + n] = s_row[i];
+        if (threadIdx.x == 0) {
+            int n = 0;
+            for (int i = 0; i < count && n < KP; ++i) {
+                const int d = s_doc[i];
+                bool dup = false;
+                for (int j = 0; j < n; ++j) dup |= (sel_doc[j] == d);
+                if (dup) continue;
+                sel_row[n] = s_row[i];
+                sel_doc[n] = d;
+                if (p.cand_score) {
+                    p.cand_score[(size_t)q * KP + n] = s_score[i];
+                    p.cand_row[(size_t)q * KP + n] = s_row[i];
+                }
+                ++n;
             }
-            ++n;
+            if (p.cand_score)
+                for (int i = n; i < KP; ++i) {
+                    p.cand_score[(size_t)q * KP + i] = -INFINITY;
+                    p.cand_row[(size_t)q * KP + i] = -1;
+                }
+            sel_n = n;
         }
-        if (p.cand_score)
-            for (int i = n; i < KP; ++i) {
-                p.cand_score[(size_t)q * KP + i] = -INFINITY;
-                p.cand_row[(size_t)q * KP + i] = -1;
-            }
-        sel_n = n;
+        __syncthreads();
+        // duplicates of one document across lists can leave fewer than KP distinct documents above the bound:
+        // fall back to the unfiltered merge
+        if (sel_n >= KP || s_count >= s_valid) break;
+        __syncthreads();
     }
-    __syncthreads();
     // exact re-score: lane l accumulates elements i = 32 j + l in ascending j (fp64), partials are then added in
     // ascending lane order.  oracle/score_oracle.c restates exactly this order.
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -888,13 +925,13 @@ int b200_index_search_device(b200_index* ix, const float* d_q, int nq, int k, in
     });
 }
 
-int b200_index_set_stream(b200_index* ix, void* cuda_stream) {
+int b200_index_set_stream(b200_index* ix, void* cuda_stream, int use_external) {
     return guarded([&] {
         MB_CHECK_ARG(ix != nullptr, "index is NULL");
         std::lock_guard<std::mutex> lk(ix->mu);
         DeviceGuard g(ix->device);
         MB_CUDA(cudaStreamSynchronize(ix->stream));
-        ix->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ix->own_stream;
+        ix->stream = use_external ? reinterpret_cast<cudaStream_t>(cuda_stream) : ix->own_stream;
     });
 }
 

@@ -111,7 +111,9 @@ class RowStore:
                                                    C.c_void_p(d_score_ptr), 1 if sync else 0))
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        N.check(self._lib.b200_index_set_stream(self._handle(), C.c_void_p(cuda_stream) if cuda_stream else None))
+        """cuda_stream: a cudaStream_t handle (0 = legacy default stream); None restores the private stream."""
+        N.check(self._lib.b200_index_set_stream(self._handle(), C.c_void_p(cuda_stream or 0),
+                                                0 if cuda_stream is None else 1))
 
     def last_timing(self) -> Tuple[float, float]:
         a, b = C.c_float(0), C.c_float(0)
@@ -269,7 +271,9 @@ class Encoder:
                                                           1 if sync else 0))
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        N.check(self._lib.b200_model_set_stream(self._handle(), C.c_void_p(cuda_stream) if cuda_stream else None))
+        """cuda_stream: a cudaStream_t handle (0 = legacy default stream); None restores the private stream."""
+        N.check(self._lib.b200_model_set_stream(self._handle(), C.c_void_p(cuda_stream or 0),
+                                                0 if cuda_stream is None else 1))
 
     def set_profiling(self, on: bool) -> None:
         N.check(self._lib.b200_model_set_profiling(self._handle(), 1 if on else 0))
