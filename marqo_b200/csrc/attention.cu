@@ -1,5 +1,7 @@
 #include "attention.cuh"
 
+#include <cstdlib>
+
 namespace mb {
 namespace attention {
 
@@ -228,6 +230,12 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 void launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
             cudaStream_t stream) {
     if (B <= 0 || S <= 0) return;
+    // TEMPORARY A/B switch while the tcgen05 kernel is being validated on hardware
+    static const bool legacy = getenv("MARQO_B200_ATTN_LEGACY") != nullptr;
+    if (!legacy) {
+        launch_tc(qkv, out, B, S, W, H, mask, kv_len, stream);
+        return;
+    }
     if (W != H * HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);
     const dim3 grid((S + BQ - 1) / BQ, H, B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;  // 1/sqrt(64) * log2(e)

@@ -13,5 +13,9 @@ enum Mask { MASK_NONE = 0, MASK_CAUSAL = 1, MASK_KEYLEN = 2 };
 void launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
             cudaStream_t stream);
 
+// tcgen05 / TMEM implementation (attention_tc.cu)
+void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+               cudaStream_t stream);
+
 }  // namespace attention
 }  // namespace mb

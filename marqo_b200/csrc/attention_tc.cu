@@ -1,0 +1,294 @@
+// tcgen05 flash attention (head_dim 64, S <= a few thousand, bf16 in / fp32 softmax / bf16 out).
+//
+// One CTA = one (batch, head, 128-query block).  Warp 0: TMA producer (Q once, K/V blocks of 128 keys through a
+// 2-stage ring, all 128B-swizzled straight from the packed qkv matrix).  Warp 1: single-thread tcgen05.mma issuer:
+//   S = Q K_j^T   (M=128, N=128, K=64;  A, B K-major)          -> TMEM columns [0,128)
+//   O += P_j V_j  (M=128, N=64,  K=128; A = P K-major from smem, B = V MN-major as loaded)  -> TMEM columns [128,192)
+// Warps 2-5: softmax, ONE THREAD PER QUERY ROW (TMEM lane == row): two passes over the row's 128 scores in TMEM
+// (max, then exp2 / sum / bf16 P written to smem in the UMMA K-major swizzled layout), running-max rescale of the O
+// accumulator through tcgen05.ld/st, final 1/l scaling and the bf16 store.  112 KB smem + 256 TMEM columns per CTA ->
+// two CTAs per SM, so one CTA's softmax overlaps the other's MMAs.
+#include "attention.cuh"
+#include "ptx.cuh"
+
+namespace mb {
+namespace attention {
+
+namespace tc {
+
+constexpr int HD = 64;
+constexpr int BQ = 128;
+constexpr int BKV = 128;
+constexpr int THREADS = 192;
+constexpr int KV_STAGES = 2;
+constexpr uint32_t Q_BYTES = BQ * HD * 2;        // 16 KB
+constexpr uint32_t KV_TILE_BYTES = BKV * HD * 2;  // 16 KB each for K and V
+constexpr uint32_t P_BYTES = BQ * BKV * 2;        // 32 KB (two 64-key K-major chunks)
+constexpr uint32_t SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES + 128;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t S_COL = 0, O_COL = 128;
+
+template <int MASK>
+__global__ void __launch_bounds__(THREADS, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __restrict__ out, int S, int W,
+                    const int32_t* __restrict__ kv_len, float scale_log2e) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* sQ = smem;
+    uint8_t* sKV = sQ + Q_BYTES;                       // stage s: K at sKV + s*32K, V at +16K
+    uint8_t* sP = sKV + KV_STAGES * 2 * KV_TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;    // [2]
+    uint64_t* kv_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_free = bars + 6;
+    uint64_t* p_full = bars + 7;
+    uint64_t* pv_done = bars + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BQ;
+    if ((ptx::smem_u32(smem) & 1023u) != 0) __trap();  // the swizzled tiles need 1024-byte alignment
+
+    int len = S;
+    if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[b], 0));
+    int kend = len;
+    if (MASK == MASK_CAUSAL) kend = min(len, q0 + BQ);
+    const int nkb = (kend + BKV - 1) / BKV;
+    const int row_base = b * S;  // first row of this sequence in the packed [B*S, 3W] matrix
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap);
+        ptx::mbar_init(q_full, 1);
+        for (int i = 0; i < KV_STAGES; ++i) {
+            ptx::mbar_init(&kv_full[i], 1);
+            ptx::mbar_init(&kv_empty[i], 1);
+        }
+        ptx::mbar_init(s_full, 1);
+        ptx::mbar_init(s_free, 4);
+        ptx::mbar_init(p_full, 4);
+        ptx::mbar_init(pv_done, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc_n<TMEM_COLS>(tmem_slot);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(q_full, Q_BYTES);
+            ptx::tma_load_2d(sQ, &tmap, q_full, h * HD, row_base + q0, ptx::kEvictNormal);
+            for (int j = 0; j < nkb; ++j) {
+                const int st = j & 1;
+                ptx::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * KV_TILE_BYTES);
+                uint8_t* dst = sKV + (size_t)st * 2 * KV_TILE_BYTES;
+                ptx::tma_load_2d(dst, &tmap, &kv_full[st], W + h * HD, row_base + j * BKV, ptx::kEvictLast);
+                ptx::tma_load_2d(dst + KV_TILE_BYTES, &tmap, &kv_full[st], 2 * W + h * HD, row_base + j * BKV,
+                                 ptx::kEvictLast);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc_s = ptx::make_idesc_f16_major(1, BQ, BKV, 0, 0);
+        constexpr uint32_t idesc_o = ptx::make_idesc_f16_major(1, BQ, HD, 0, 1);  // B (= V) is MN-major
+        ptx::mbar_wait(q_full, 0);
+        for (int j = 0; j < nkb; ++j) {
+            const int st = j & 1;
+            const uint32_t par = j & 1;
+            ptx::mbar_wait(&kv_full[st], (j >> 1) & 1);
+            if (j > 0) ptx::mbar_wait(s_free, par ^ 1);  // softmax has finished reading S of block j-1
+            ptx::tc_fence_after();
+            const uint32_t k_base = ptx::smem_u32(sKV + (size_t)st * 2 * KV_TILE_BYTES);
+            const uint32_t v_base = k_base + KV_TILE_BYTES;
+            if (lane == 0) {
+                const uint32_t q_base = ptx::smem_u32(sQ);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    ptx::umma_f16(tmem_base + S_COL, ptx::make_desc_k_sw128(q_base + k * 32),
+                                  ptx::make_desc_k_sw128(k_base + k * 32), idesc_s, k != 0 ? 1u : 0u);
+                ptx::umma_commit(s_full);
+            }
+            __syncwarp();
+            ptx::mbar_wait(p_full, par);  // P_j is in smem and O has been rescaled
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                const uint32_t p_base = ptx::smem_u32(sP);
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    const uint32_t a_addr = p_base + (k >> 2) * (BQ * 128) + (k & 3) * 32;
+                    const uint32_t b_addr = v_base + k * 16 * 128;  // 16 keys = two 8-key swizzle atoms
+                    ptx::umma_f16(tmem_base + O_COL, ptx::make_desc_k_sw128(a_addr),
+                                  ptx::make_desc_mn_sw128(b_addr, 8192, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&kv_empty[st]);
+                ptx::umma_commit(pv_done);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax: thread == query row
+        const int sp = warp & 3;
+        const int r = sp * 32 + lane;  // row within the tile == TMEM lane
+        const int qrow = q0 + r;       // position in the sequence
+        const uint32_t lane_addr = tmem_base + (uint32_t(sp * 32) << 16);
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nkb; ++j) {
+            const uint32_t par = j & 1;
+            ptx::mbar_wait(s_full, par);
+            ptx::tc_fence_after();
+            int limit = len - j * BKV;  // keys with index >= limit are masked
+            if (MASK == MASK_CAUSAL) limit = min(limit, qrow - j * BKV + 1);
+            // pass 1: row maximum of this block
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < BKV / 32; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (c * 32 + i < limit) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            mx *= scale_log2e;  // scale > 0: max commutes with the scaling
+            const float m_new = fmaxf(m_run, mx);
+            const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+            const float alpha = exp2f(m_run - m_safe);  // 0 on the first block
+            if (j > 0) ptx::mbar_wait(pv_done, par ^ 1);  // P buffer and O accumulator are free again
+            // pass 2: p = exp2(s - m), row sum, bf16 P into the K-major 128B-swizzled A-operand layout
+            float lsum = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < BKV / 32; ++c) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, v);
+                ptx::tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = c * 32 + i < limit ? exp2f(__uint_as_float(v[i]) * scale_log2e - m_safe) : 0.f;
+                    const float p1 = c * 32 + i + 1 < limit ? exp2f(__uint_as_float(v[i + 1]) * scale_log2e - m_safe) : 0.f;
+                    lsum += p0 + p1;
+                    __nv_bfloat162 t2 = __floats2bfloat162_rn(p0, p1);
+                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+                }
+                // keys c*32 .. c*32+31 -> chunk (c >> 1), 16-byte units (c & 1) * 4 .. +3 of row r
+                uint8_t* rowp = sP + (size_t)(c >> 1) * (BQ * 128) + (size_t)r * 128;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int unit = (c & 1) * 4 + u;
+                    *reinterpret_cast<uint4*>(rowp + ((unit ^ (r & 7)) << 4)) =
+                        make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                }
+            }
+            l_run = l_run * alpha + lsum;
+            m_run = m_new;
+            // S has been consumed: the MMA warp may overwrite it with the next block's scores
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(s_free);
+            if (j > 0) {
+                // rescale the running output by alpha (thread-local: lane == row)
+#pragma unroll 1
+                for (int c = 0; c < HD / 32; ++c) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + c * 32, v);
+                    ptx::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                    ptx::tmem_st_32x32b_x32(lane_addr + O_COL + c * 32, v);
+                }
+                ptx::tmem_st_wait();
+            }
+            ptx::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(p_full);
+        }
+        // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
+        if (nkb > 0) {
+            ptx::mbar_wait(pv_done, (nkb - 1) & 1);
+            ptx::tc_fence_after();
+        }
+        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+        __nv_bfloat16* dst = out + ((size_t)row_base + qrow) * W + h * HD;
+#pragma unroll 1
+        for (int c = 0; c < HD / 32; ++c) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + c * 32, v);
+                ptx::tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0u;
+            }
+            if (qrow < S) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+                }
+                uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) d4[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace tc
+
+void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+               cudaStream_t stream) {
+    if (B <= 0 || S <= 0) return;
+    if (W != H * tc::HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);
+    static bool configured = false;
+    if (!configured) {
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tc::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tc::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_KEYLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)tc::SMEM_BYTES));
+        configured = true;
+    }
+    // one tensor map over the packed [B*S, 3W] matrix serves Q, K and V tiles (64 columns x 128 rows, 128B swizzle);
+    // rows past the end of the matrix are zero-filled, rows of the next sequence are masked by key index
+    CUtensorMap tmap = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,
+                                    (uint64_t)3 * W * 2, tc::HD, tc::BQ, CU_TENSOR_MAP_SWIZZLE_128B);
+    const dim3 grid((S + tc::BQ - 1) / tc::BQ, H, B);
+    const float scale_log2e = 0.125f * 1.4426950408889634f;
+    switch (mask) {
+        case MASK_NONE:
+            tc::attention_tc_kernel<MASK_NONE><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, out, S, W, kv_len,
+                                                                                             scale_log2e);
+            break;
+        case MASK_CAUSAL:
+            tc::attention_tc_kernel<MASK_CAUSAL><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, out, S, W, kv_len,
+                                                                                               scale_log2e);
+            break;
+        case MASK_KEYLEN:
+            if (!kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
+            tc::attention_tc_kernel<MASK_KEYLEN><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, out, S, W, kv_len,
+                                                                                               scale_log2e);
+            break;
+        default:
+            fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);
+    }
+    MB_CUDA(cudaGetLastError());
+}
+
+}  // namespace attention
+}  // namespace mb

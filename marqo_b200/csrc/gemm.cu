@@ -10,7 +10,8 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int EPI_WARPS = 8;  // two warps per TMEM sub-partition, each draining one half of the tile's columns
+constexpr int THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;
 constexpr int SMEM_LIMIT = 232448;
@@ -69,7 +70,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
         for (int i = 0; i < ACC_STAGES; ++i) {
             ptx::mbar_init(&tfull[i], 1);
-            ptx::mbar_init(&tempty[i], 4);
+            ptx::mbar_init(&tempty[i], EPI_WARPS);
         }
         ptx::fence_barrier_init();
     }
@@ -136,13 +137,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         }
     } else {
         // ---------------------------------------------------------------- epilogue (TMEM -> regs -> global)
+        // A warp may only read the TMEM lanes of sub-partition (warp % 4); the two warps that share a sub-partition
+        // split the tile's columns in halves, so 8 warps drain one 128 x BN accumulator.
         const int sp = warp & 3;
+        const int half = (warp - 2) >> 2;
+        constexpr int HALF_COLS = BN / 2 >= 32 ? BN / 2 : 32;
+        constexpr int CHUNKS = HALF_COLS / 32;
+        const bool has_cols = half * HALF_COLS < BN;  // BN = 32 would leave the second half empty
         const Epilogue& ep = p.ep;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int m0 = (t / p.tiles_n) * BM;
-            const int nt0 = (t % p.tiles_n) * BN;
+            const int nt0 = (t % p.tiles_n) * BN + half * HALF_COLS;
             const int row = m0 + sp * 32 + lane;
             const bool row_ok = row < p.M;
             long long orow = row;
@@ -152,72 +159,84 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 orow = (long long)b * (ep.remap_group + 1) + 1 + i;
                 brow = 1 + i;
             }
+            if (ep.residual && row_ok && has_cols) {
+                // pull this thread's residual segment towards L2 while the MMAs of the tile are still running
+                const char* r = reinterpret_cast<const char*>(ep.residual + (size_t)row * ep.ldr + nt0);
+#pragma unroll
+                for (int l = 0; l < HALF_COLS * 4 / 128; ++l)
+                    if (nt0 + l * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + l * 128));
+            }
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < CHUNKS; ++c) {
                 uint32_t v[32];
-                ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(sp * 32) << 16) + acc * BN + c * 32, v);
-                ptx::tmem_ld_wait();
-                if (c == BN / 32 - 1) {
-                    // accumulator fully drained into registers: hand it back to the MMA warp
+                if (has_cols) {
+                    ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(sp * 32) << 16) + acc * BN + half * HALF_COLS + c * 32, v);
+                    ptx::tmem_ld_wait();
+                }
+                if (c == CHUNKS - 1) {
+                    // this warp's share of the accumulator is in registers: hand it back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
                 }
                 const int n0 = nt0 + c * 32;
-                if (row_ok && n0 < p.N) {
-                float f[32];
+                if (has_cols && row_ok && n0 < p.N) {
+                    float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (ep.bias) {
-                    const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (ep.bias) {
+                        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = __ldg(b4 + j);
-                        f[4 * j] += b.x;
-                        f[4 * j + 1] += b.y;
-                        f[4 * j + 2] += b.z;
-                        f[4 * j + 3] += b.w;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(b4 + j);
+                            f[4 * j] += b.x;
+                            f[4 * j + 1] += b.y;
+                            f[4 * j + 2] += b.z;
+                            f[4 * j + 3] += b.w;
+                        }
                     }
-                }
-                if (ep.act != ACT_NONE) {
+                    if (ep.act != ACT_NONE) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
-                }
-                if (ep.rowbias) {
-                    const float4* r4 = reinterpret_cast<const float4*>(ep.rowbias + (size_t)brow * p.N + n0);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = __ldg(r4 + j);
-                        f[4 * j] += b.x;
-                        f[4 * j + 1] += b.y;
-                        f[4 * j + 2] += b.z;
-                        f[4 * j + 3] += b.w;
+                        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
                     }
-                }
-                if (ep.residual) {
-                    const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + n0);
+                    if (ep.rowbias) {
+                        const float4* r4 = reinterpret_cast<const float4*>(ep.rowbias + (size_t)brow * p.N + n0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = r4[j];
-                        f[4 * j] += b.x;
-                        f[4 * j + 1] += b.y;
-                        f[4 * j + 2] += b.z;
-                        f[4 * j + 3] += b.w;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(r4 + j);
+                            f[4 * j] += b.x;
+                            f[4 * j + 1] += b.y;
+                            f[4 * j + 2] += b.z;
+                            f[4 * j + 3] += b.w;
+                        }
                     }
-                }
-                if (ep.out_fp32) {
-                    float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0);
+                    if (ep.residual) {
+                        const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + n0);
+                        float4 rr[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                } else {
-                    uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)orow * ep.ldo + n0);
+                        for (int j = 0; j < 8; ++j) rr[j] = r4[j];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-                }
+                        for (int j = 0; j < 8; ++j) {
+                            f[4 * j] += rr[j].x;
+                            f[4 * j + 1] += rr[j].y;
+                            f[4 * j + 2] += rr[j].z;
+                            f[4 * j + 3] += rr[j].w;
+                        }
+                    }
+                    if (ep.out_fp32) {
+                        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+                        uint4* o4 =
+                            reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)orow * ep.ldo + n0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                    }
                 }
             }
             if (++acc == ACC_STAGES) {

@@ -34,6 +34,8 @@ constexpr int BLOCK_K = 64;     // fp16 elements per 128-byte swizzle row
 constexpr int MQ = 64;          // queries per pass (UMMA_M)
 constexpr int UMMA_K = 16;
 constexpr int KP = 16;          // candidates kept per list
+constexpr int SLACK = 6;        // candidates beyond k that absorb approximate-vs-exact reordering at the boundary
+constexpr int K_SINGLE = KP - SLACK;  // largest k answered by one pass over the corpus
 constexpr int ACC_STAGES = 4;   // TMEM accumulators (4 x 128 fp32 columns = all 512 columns)
 constexpr int THREADS = 192;    // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr uint32_t STAGE_BYTES = TILE_N * BLOCK_K * 2;
@@ -532,6 +534,16 @@ __global__ void tombstone_kernel(int32_t* doc_of_row, int64_t n, int32_t doc) {
     if (i < n && doc_of_row[i] == doc) doc_of_row[i] = -1;
 }
 
+// bound for the next round = the last kept candidate of this round (approximate order); a short list means the
+// corpus is exhausted for that query: -inf makes every later comparison fail.
+__global__ void next_bound_kernel(const float* cand_score, const int32_t* cand_row, float* bound_score,
+                                  int32_t* bound_row) {
+    const int q = threadIdx.x;
+    const int r = cand_row[q * KP + KP - 1];
+    bound_score[q] = r >= 0 ? cand_score[q * KP + KP - 1] : -INFINITY;
+    bound_row[q] = r >= 0 ? r : INT_MAX;
+}
+
 __global__ void fill_empty_kernel(int32_t* out_doc, int32_t* out_row, double* out_score, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -567,6 +579,8 @@ struct b200_index {
     int32_t* o_doc = nullptr;      // [MQ, KP] device outputs for the host API
     int32_t* o_row = nullptr;
     double* o_score = nullptr;
+    float *cand_score = nullptr, *bound_score = nullptr;   // [MQ, KP] / [MQ]: multi-round search (k > K_SINGLE)
+    int32_t *cand_row = nullptr, *bound_row = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -589,6 +603,10 @@ void index_free(b200_index* ix) {
     cudaFree(ix->o_doc);
     cudaFree(ix->o_row);
     cudaFree(ix->o_score);
+    cudaFree(ix->cand_score);
+    cudaFree(ix->cand_row);
+    cudaFree(ix->bound_score);
+    cudaFree(ix->bound_row);
     for (auto& e : ix->ev)
         if (e) cudaEventDestroy(e);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
@@ -660,6 +678,10 @@ b200_index* index_new(int device, int dim, int metric, int64_t capacity_rows) {
         cuda_alloc((void**)&ix->o_doc, (size_t)MQ * KP * sizeof(int32_t));
         cuda_alloc((void**)&ix->o_row, (size_t)MQ * KP * sizeof(int32_t));
         cuda_alloc((void**)&ix->o_score, (size_t)MQ * KP * sizeof(double));
+        cuda_alloc((void**)&ix->cand_score, (size_t)MQ * KP * sizeof(float));
+        cuda_alloc((void**)&ix->cand_row, (size_t)MQ * KP * sizeof(int32_t));
+        cuda_alloc((void**)&ix->bound_score, (size_t)MQ * sizeof(float));
+        cuda_alloc((void**)&ix->bound_row, (size_t)MQ * sizeof(int32_t));
         ensure_capacity(ix, std::max<int64_t>(capacity_rows, TILE_N));
         MB_CUDA(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         MB_CUDA(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -692,7 +714,8 @@ void add_rows_device(b200_index* ix, const float* d_vecs, const int32_t* d_doc_i
 
 // One pass over the corpus for <= MQ queries already converted into ix->qh.
 void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_out_row, double* d_out_score,
-                  bool record_timing) {
+                  bool record_timing, const float* bound_score = nullptr, const int32_t* bound_row = nullptr,
+                  float* cand_score = nullptr, int32_t* cand_row = nullptr) {
     const int total = nq * k;
     if (ix->n_rows == 0) {
         fill_empty_kernel<<<(total + 255) / 256, 256, 0, ix->stream>>>(d_out_doc, d_out_row, d_out_score, total);
@@ -718,8 +741,8 @@ void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_
     sp.num_stages = stages;
     sp.nq = nq;
     sp.doc_of_row = ix->doc_of_row;
-    sp.bound_score = nullptr;
-    sp.bound_row = nullptr;
+    sp.bound_score = bound_score;
+    sp.bound_row = bound_row;
     sp.out_score = ix->list_score;
     sp.out_row = ix->list_row;
     sp.out_doc = ix->list_doc;
@@ -749,14 +772,83 @@ void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_
     mp.out_doc = d_out_doc;
     mp.out_row = d_out_row;
     mp.out_score = d_out_score;
-    mp.cand_score = nullptr;
-    mp.cand_row = nullptr;
+    mp.cand_score = cand_score;
+    mp.cand_row = cand_row;
     merge_kernel<<<nq, MERGE_THREADS, (size_t)sort_n * 12, ix->stream>>>(mp);
     MB_CUDA(cudaGetLastError());
     if (record_timing) {
         MB_CUDA(cudaEventRecord(ix->ev[2], ix->stream));
         ix->timing_valid = true;
     }
+}
+
+// k beyond the single-pass limit: repeated scans, each restricted to rows strictly after the previous round's last
+// candidate in the (approximate score desc, row asc) order, until k + SLACK distinct documents are collected.
+// Every round re-scores its candidates exactly, so the final order is again (exact score desc, doc asc).
+void search_group_rounds(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_out_row, double* d_out_score) {
+    struct Hit {
+        double s;
+        int32_t doc, row;
+    };
+    std::vector<std::vector<Hit>> acc(nq);
+    std::vector<char> done(nq, 0);
+    std::vector<int32_t> h_doc((size_t)MQ * KP), h_row((size_t)MQ * KP);
+    std::vector<double> h_score((size_t)MQ * KP);
+    std::vector<int32_t> seen;
+    const int max_rounds = 20000;
+    for (int round = 0;; ++round) {
+        if (round >= max_rounds) fail(B200_ERR_INTERNAL, "search did not converge in %d rounds", max_rounds);
+        search_group(ix, nq, KP, ix->o_doc, ix->o_row, ix->o_score, round == 0, round == 0 ? nullptr : ix->bound_score,
+                     round == 0 ? nullptr : ix->bound_row, ix->cand_score, ix->cand_row);
+        if (ix->n_rows == 0) break;
+        next_bound_kernel<<<1, MQ, 0, ix->stream>>>(ix->cand_score, ix->cand_row, ix->bound_score, ix->bound_row);
+        MB_CUDA(cudaGetLastError());
+        MB_CUDA(cudaMemcpyAsync(h_doc.data(), ix->o_doc, (size_t)nq * KP * 4, cudaMemcpyDeviceToHost, ix->stream));
+        MB_CUDA(cudaMemcpyAsync(h_row.data(), ix->o_row, (size_t)nq * KP * 4, cudaMemcpyDeviceToHost, ix->stream));
+        MB_CUDA(cudaMemcpyAsync(h_score.data(), ix->o_score, (size_t)nq * KP * 8, cudaMemcpyDeviceToHost, ix->stream));
+        MB_CUDA(cudaStreamSynchronize(ix->stream));
+        bool all_done = true;
+        for (int q = 0; q < nq; ++q) {
+            if (done[q]) continue;
+            int valid = 0;
+            for (int i = 0; i < KP; ++i) {
+                const size_t o = (size_t)q * KP + i;
+                if (h_doc[o] < 0) continue;
+                ++valid;
+                acc[q].push_back({h_score[o], h_doc[o], h_row[o]});
+            }
+            seen.clear();
+            for (const Hit& h : acc[q]) seen.push_back(h.doc);
+            std::sort(seen.begin(), seen.end());
+            const int distinct = (int)(std::unique(seen.begin(), seen.end()) - seen.begin());
+            if (valid < KP || distinct >= k + SLACK) done[q] = 1;
+            all_done = all_done && done[q];
+        }
+        if (all_done) break;
+    }
+    std::vector<int32_t> o_doc((size_t)nq * k, -1), o_row((size_t)nq * k, -1);
+    std::vector<double> o_score((size_t)nq * k, -std::numeric_limits<double>::infinity());
+    for (int q = 0; q < nq; ++q) {
+        std::vector<Hit>& v = acc[q];
+        // best chunk per document: (score desc, row asc), then documents by (score desc, doc asc)
+        std::sort(v.begin(), v.end(), [](const Hit& a, const Hit& b) {
+            return a.doc < b.doc || (a.doc == b.doc && (a.s > b.s || (a.s == b.s && a.row < b.row)));
+        });
+        size_t w = 0;
+        for (size_t i = 0; i < v.size(); ++i)
+            if (i == 0 || v[i].doc != v[i - 1].doc) v[w++] = v[i];
+        v.resize(w);
+        std::sort(v.begin(), v.end(), [](const Hit& a, const Hit& b) { return a.s > b.s || (a.s == b.s && a.doc < b.doc); });
+        for (int i = 0; i < k && i < (int)v.size(); ++i) {
+            o_doc[(size_t)q * k + i] = v[i].doc;
+            o_row[(size_t)q * k + i] = v[i].row;
+            o_score[(size_t)q * k + i] = v[i].s;
+        }
+    }
+    MB_CUDA(cudaMemcpyAsync(d_out_doc, o_doc.data(), o_doc.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+    MB_CUDA(cudaMemcpyAsync(d_out_row, o_row.data(), o_row.size() * 4, cudaMemcpyHostToDevice, ix->stream));
+    MB_CUDA(cudaMemcpyAsync(d_out_score, o_score.data(), o_score.size() * 8, cudaMemcpyHostToDevice, ix->stream));
+    MB_CUDA(cudaStreamSynchronize(ix->stream));
 }
 
 void search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_out_doc, int32_t* d_out_row,
@@ -766,8 +858,12 @@ void search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_o
         convert_rows_kernel<<<MQ / 8, 256, 0, ix->stream>>>(d_q + (size_t)q0 * ix->dim, ix->qh, g, ix->dim, MQ,
                                                             ix->metric == B200_METRIC_ANGULAR);
         MB_CUDA(cudaGetLastError());
-        search_group(ix, g, k, d_out_doc + (size_t)q0 * k, d_out_row + (size_t)q0 * k, d_out_score + (size_t)q0 * k,
-                     q0 + MQ >= nq);
+        if (k <= K_SINGLE)
+            search_group(ix, g, k, d_out_doc + (size_t)q0 * k, d_out_row + (size_t)q0 * k, d_out_score + (size_t)q0 * k,
+                         q0 + MQ >= nq);
+        else
+            search_group_rounds(ix, g, k, d_out_doc + (size_t)q0 * k, d_out_row + (size_t)q0 * k,
+                                d_out_score + (size_t)q0 * k);
     }
 }
 
@@ -776,7 +872,7 @@ void check_search_args(b200_index* ix, const void* q, int nq, int k, const void*
     MB_CHECK_ARG(q && a && b && c, "NULL buffer");
     MB_CHECK_ARG(nq > 0, "nq must be positive (got %d)", nq);
     MB_CHECK_ARG(k > 0, "k must be positive (got %d)", k);
-    if (k > KP) fail(B200_ERR_UNSUPPORTED, "k = %d exceeds the single-pass limit of %d", k, KP);
+    MB_CHECK_ARG(k <= 10000, "k = %d exceeds 10000 (Marqo's own limit + offset cap, tensor_search.py:1568-1588)", k);
 }
 
 }  // namespace
@@ -898,19 +994,36 @@ int b200_index_search(b200_index* ix, const float* q, int nq, int k, int32_t* ou
         check_search_args(ix, q, nq, k, out_doc, out_row, out_score);
         std::lock_guard<std::mutex> lk(ix->mu);
         DeviceGuard g(ix->device);
-        for (int q0 = 0; q0 < nq; q0 += MQ) {
-            const int gq = std::min(MQ, nq - q0);
-            MB_CUDA(cudaMemcpyAsync(ix->q_stage, q + (size_t)q0 * ix->dim, (size_t)gq * ix->dim * sizeof(float),
-                                    cudaMemcpyHostToDevice, ix->stream));
-            search_device(ix, ix->q_stage, gq, k, ix->o_doc, ix->o_row, ix->o_score);
-            MB_CUDA(cudaMemcpyAsync(out_doc + (size_t)q0 * k, ix->o_doc, (size_t)gq * k * sizeof(int32_t),
-                                    cudaMemcpyDeviceToHost, ix->stream));
-            MB_CUDA(cudaMemcpyAsync(out_row + (size_t)q0 * k, ix->o_row, (size_t)gq * k * sizeof(int32_t),
-                                    cudaMemcpyDeviceToHost, ix->stream));
-            MB_CUDA(cudaMemcpyAsync(out_score + (size_t)q0 * k, ix->o_score, (size_t)gq * k * sizeof(double),
-                                    cudaMemcpyDeviceToHost, ix->stream));
-            MB_CUDA(cudaStreamSynchronize(ix->stream));
+        int32_t *dd = ix->o_doc, *dr = ix->o_row;
+        double* ds = ix->o_score;
+        void* tmp[3] = {nullptr, nullptr, nullptr};
+        if (k > KP) {  // the resident [MQ, KP] output block is too small for a large k
+            cuda_alloc(&tmp[0], (size_t)MQ * k * sizeof(int32_t));
+            cuda_alloc(&tmp[1], (size_t)MQ * k * sizeof(int32_t));
+            cuda_alloc(&tmp[2], (size_t)MQ * k * sizeof(double));
+            dd = (int32_t*)tmp[0];
+            dr = (int32_t*)tmp[1];
+            ds = (double*)tmp[2];
         }
+        try {
+            for (int q0 = 0; q0 < nq; q0 += MQ) {
+                const int gq = std::min(MQ, nq - q0);
+                MB_CUDA(cudaMemcpyAsync(ix->q_stage, q + (size_t)q0 * ix->dim, (size_t)gq * ix->dim * sizeof(float),
+                                        cudaMemcpyHostToDevice, ix->stream));
+                search_device(ix, ix->q_stage, gq, k, dd, dr, ds);
+                MB_CUDA(cudaMemcpyAsync(out_doc + (size_t)q0 * k, dd, (size_t)gq * k * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, ix->stream));
+                MB_CUDA(cudaMemcpyAsync(out_row + (size_t)q0 * k, dr, (size_t)gq * k * sizeof(int32_t),
+                                        cudaMemcpyDeviceToHost, ix->stream));
+                MB_CUDA(cudaMemcpyAsync(out_score + (size_t)q0 * k, ds, (size_t)gq * k * sizeof(double),
+                                        cudaMemcpyDeviceToHost, ix->stream));
+                MB_CUDA(cudaStreamSynchronize(ix->stream));
+            }
+        } catch (...) {
+            for (void* t : tmp) cudaFree(t);
+            throw;
+        }
+        for (void* t : tmp) cudaFree(t);
     });
 }
 

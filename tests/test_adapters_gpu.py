@@ -1,0 +1,194 @@
+"""GPU tests of the reference-facing adapters: vectorise() through the loader classes (B1) and the VespaClient-shaped
+GpuTensorIndex (B2), against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoders as E
+
+pytestmark = pytest.mark.gpu
+
+TINY_BERT_ARCH = dict(width=128, layers=2, heads=2, mlp=512, vocab=1000, max_pos=64, type_vocab=2, pool="mean")
+TINY_CLIP_ARCH = dict(embed_dim=128, act="gelu", mean=E.OPENAI_CLIP_MEAN, std=E.OPENAI_CLIP_STD,
+                      vision=dict(width=128, layers=2, heads=2, mlp=512, patch=32, image_size=224),
+                      text=dict(width=128, layers=2, heads=2, mlp=512, ctx=77, vocab=1000))
+
+
+class WordTokenizer:
+    """Stand-in for AutoTokenizer (no vocab files offline): 'w<id>' words -> ids, [CLS]=2 ... [SEP]=3, pad 0."""
+
+    def __call__(self, sentences, padding=True, truncation=True, max_length=128, return_tensors="np"):
+        rows = []
+        for s in sentences:
+            ids = [2] + [5 + int(w[1:]) for w in s.split()][: max_length - 2] + [3]
+            rows.append(ids)
+        L = max(len(r) for r in rows)
+        ids = np.zeros((len(rows), L), np.int64)
+        mask = np.zeros((len(rows), L), np.int64)
+        for i, r in enumerate(rows):
+            ids[i, :len(r)] = r
+            mask[i, :len(r)] = 1
+        return {"input_ids": ids, "attention_mask": mask}
+
+
+def _cos_ok(got, ref):
+    got, ref = torch.as_tensor(np.asarray(got)).double(), torch.as_tensor(np.asarray(ref)).double()
+    cos = torch.nn.functional.cosine_similarity(got, ref)
+    assert float((1 - cos).max()) < 1e-3, float(cos.min())
+
+
+def test_vectorise_hf_loader_end_to_end(gpu_required, monkeypatch):
+    from marqo_b200 import s2_inference as s2, weights as Wt
+    s2.clear_loaded_models()
+    tok = WordTokenizer()
+    props = {"name": "tiny-bert", "dimensions": 128, "type": "hf", "tokens": 32, "arch": TINY_BERT_ARCH,
+             "random_init": 77, "tokenizer": tok}
+    rng = np.random.default_rng(0)
+    sentences = [" ".join(f"w{int(x)}" for x in rng.integers(0, 990, size=n)) for n in rng.integers(1, 45, size=21)]
+    monkeypatch.setenv("MARQO_MAX_VECTORISE_BATCH_SIZE", "8")           # 3 sub-batches, each padded to its own longest
+    out = s2.vectorise("tiny-bert", sentences, model_properties=props, device="cuda:0", normalize_embeddings=True)
+    assert isinstance(out, list) and len(out) == 21 and len(out[0]) == 128 and isinstance(out[0][0], float)
+    sd = {k: torch.from_numpy(v) for k, v in Wt.random_bert_weights(TINY_BERT_ARCH, 77).items()}
+    cfg = E.BertCfg(128, 2, 2, 512, vocab=1000, max_pos=64)
+    ref = []
+    for i in range(0, 21, 8):                                            # the reference pads per sub-batch (Appendix A)
+        t = tok(sentences[i:i + 8], max_length=32)
+        ref.append(E.bert_encode(sd, cfg, torch.from_numpy(t["input_ids"]), torch.from_numpy(t["attention_mask"])))
+    _cos_ok(out, torch.cat(ref))
+    assert np.allclose(np.linalg.norm(np.asarray(out), axis=1), 1.0, atol=1e-5)
+    one = s2.vectorise("tiny-bert", sentences[3], model_properties=props, device="cuda:0")
+    _cos_ok(one, torch.cat(ref)[3:4])                                    # str == [str] (test_encoding.py:28-60)
+    assert len(s2._available_models) == 1
+    s2.eject_model("tiny-bert", "cuda:0", props)
+    assert len(s2._available_models) == 0
+
+
+def test_vectorise_clip_loader_images_and_text(gpu_required, monkeypatch):
+    from PIL import Image
+    from marqo_b200 import s2_inference as s2, weights as Wt
+    s2.clear_loaded_models()
+    ids_table = {}
+
+    def clip_tok(texts):
+        out = np.zeros((len(texts), 77), np.int64)
+        for i, t in enumerate(texts):
+            w = [int(x) for x in t.split()]
+            out[i, 0] = 998
+            out[i, 1:1 + len(w)] = w
+            out[i, 1 + len(w)] = 999
+        return out
+
+    props = {"name": "tiny-clip", "dimensions": 128, "type": "open_clip", "arch": TINY_CLIP_ARCH, "random_init": 5,
+             "tokenizer": clip_tok, "max_batch": 8}
+    rng = np.random.default_rng(1)
+    raw = [rng.integers(0, 256, size=(224, 224, 3), dtype=np.uint8) for _ in range(5)]
+    raw.append(rng.integers(0, 256, size=(260, 330, 3), dtype=np.uint8))        # one odd-sized image: resize path
+    pil = [Image.fromarray(a) for a in raw]
+    sd = {k: torch.from_numpy(v) for k, v in Wt.random_clip_weights(TINY_CLIP_ARCH, 5).items()}
+    cfg = E.tiny_clip()
+    ref = E.clip_encode_image(sd, cfg, torch.stack([E.clip_preprocess_pil(p) for p in pil]))
+    monkeypatch.setenv("MARQO_MAX_VECTORISE_BATCH_SIZE", "4")
+    out = s2.vectorise("tiny-clip", pil, model_properties=props, device="cuda:0", modality=s2.Modality.IMAGE)
+    _cos_ok(out, ref)
+    # what the download threads hand over: model.preprocess(pil) tensors (add_docs.py:129-134)
+    key = next(iter(s2._available_models))
+    model = s2._available_models[key]["model"]
+    pre = [model.preprocess(p) for p in pil]
+    assert pre[0].dtype == torch.uint8 and tuple(pre[0].shape) == (224, 224, 3)
+    out2 = s2.vectorise("tiny-clip", pre, model_properties=props, device="cuda:0", modality=s2.Modality.IMAGE)
+    assert out2 == out
+    # already-preprocessed float CHW tensors pass through unchanged (abstract_clip_model.py:108-111)
+    chw = [E.clip_preprocess_pil(p) for p in pil[:3]]
+    _cos_ok(s2.vectorise("tiny-clip", chw, model_properties=props, device="cuda:0", modality=s2.Modality.IMAGE), ref[:3])
+    # text
+    texts = ["1 2 3", "7", " ".join(str(i) for i in range(10, 60))]
+    tref = E.clip_encode_text(sd, cfg, torch.from_numpy(clip_tok(texts)))
+    _cos_ok(s2.vectorise("tiny-clip", texts, model_properties=props, device="cuda:0"), tref)
+    assert np.array_equal(model.encode_text(texts), model.encode(texts))         # test_encoding.py:334-370
+    s2.clear_loaded_models()
+
+
+def _doc(doc_id, fields, embs):
+    f = dict(fields)
+    for name, (chunks, vecs) in embs.items():
+        f[f"marqo__chunks_{name}"] = chunks
+        f[f"marqo__embeddings_{name}"] = {str(i): v.tolist() for i, v in enumerate(vecs)}
+    return {"id": doc_id, "fields": f}
+
+
+def _yql(schema, fields, k):
+    terms = " OR ".join(f"({{targetHits:{k}, approximate:False, hnsw.exploreAdditionalHits:0}}"
+                        f"nearestNeighbor(marqo__embeddings_{f}, marqo__query_embedding))" for f in fields)
+    return f"select * from {schema} where ({terms})"
+
+
+def test_gpu_tensor_index_feed_query_highlights_overwrite_delete(gpu_required):
+    from marqo_b200.gpu_tensor_index import GpuTensorIndex, gather_documents_from_response
+    rng = np.random.default_rng(3)
+    D, n = 64, 40
+
+    def unit(m):
+        x = rng.standard_normal((m, D)).astype(np.float32)
+        return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+    ix = GpuTensorIndex()
+    docs, title_vecs, body_vecs = [], {}, {}
+    for i in range(n):
+        tv, bv = unit(1), unit(int(rng.integers(1, 4)))
+        title_vecs[f"d{i}"], body_vecs[f"d{i}"] = tv, bv
+        docs.append(_doc(f"d{i}", {"marqo__id": f"d{i}", "price": i},
+                         {"title": ([f"title {i}"], tv), "body": ([f"body {i} chunk {j}" for j in range(len(bv))], bv)}))
+    resp = ix.feed_batch(docs, "s1")
+    assert not resp.errors and len(resp.responses) == n and resp.responses[0].status == 200
+    assert resp.responses[3].id == "id:s1:s1::d3"                                 # parsed with split('::')[-1]
+
+    q = body_vecs["d7"][-1] * 0.9 + 0.1 * unit(1)[0]
+    q /= np.linalg.norm(q)
+    qf = {"marqo__query_embedding": q.tolist()}
+    res = ix.query(_yql("s1", ["title", "body"], 5), hits=5, ranking="embedding_similarity", model_restrict="s1",
+                   query_features=qf)
+    # brute-force expectation on the fp16-rounded store: max over fields and chunks of 1/(2 - q.e)
+    qh = q.astype(np.float16).astype(np.float64)
+    exp = {}
+    for did in title_vecs:
+        allv = np.concatenate([title_vecs[did], body_vecs[did]]).astype(np.float16).astype(np.float64)
+        exp[did] = float((1.0 / (2.0 - allv @ qh)).max())
+    order = sorted(exp, key=lambda d: -exp[d])[:5]
+    assert [h.id.split("::")[-1] for h in res.hits] == order
+    assert abs(res.hits[0].relevance - exp[order[0]]) < 1e-9
+    assert res.root.coverage.coverage == 100
+    out = gather_documents_from_response(res)
+    assert out["hits"][0]["_id"] == "d7" and out["hits"][0]["price"] == 7
+    last = len(body_vecs["d7"]) - 1
+    assert out["hits"][0]["_highlights"] == [{"body": f"body 7 chunk {last}"}]
+    # single-field query only searches that field
+    res_t = ix.query(_yql("s1", ["title"], 3), hits=3, ranking="embedding_similarity", model_restrict="s1",
+                     query_features={"marqo__query_embedding": title_vecs["d11"][0].tolist()})
+    assert res_t.hits[0].id.endswith("::d11") and abs(res_t.hits[0].relevance - 1.0) < 2e-3
+    # offset
+    res_o = ix.query(_yql("s1", ["title", "body"], 5), hits=3, offset=2, ranking="embedding_similarity",
+                     model_restrict="s1", query_features=qf)
+    assert [h.id.split("::")[-1] for h in res_o.hits] == order[2:5]
+    # overwrite by id: the old vectors must stop matching
+    new = unit(1)
+    ix.feed_batch([_doc("d7", {"marqo__id": "d7", "price": 700}, {"title": (["new title"], new)})], "s1")
+    res2 = ix.query(_yql("s1", ["title", "body"], 5), hits=5, ranking="embedding_similarity", model_restrict="s1",
+                    query_features=qf)
+    assert "d7" not in [h.id.split("::")[-1] for h in res2.hits[:1]]
+    got = ix.get_batch(["d7", "nope"], "s1")
+    assert got.responses[0].status == 200 and got.responses[1].status == 404
+    f7 = got.responses[0].document.fields
+    assert f7["price"] == 700 and "marqo__embeddings_body" not in f7
+    np.testing.assert_array_equal(np.asarray(f7["marqo__embeddings_title"]["0"], np.float32),
+                                  new[0].astype(np.float16).astype(np.float32))
+    # delete
+    ix.delete_batch(["d11"], "s1")
+    res3 = ix.query(_yql("s1", ["title"], 3), hits=3, ranking="embedding_similarity", model_restrict="s1",
+                    query_features={"marqo__query_embedding": title_vecs["d11"][0].tolist()})
+    assert all(not h.id.endswith("::d11") for h in res3.hits)
+    assert ix.get_document_count("s1") == n - 1
+    # a bad document does not fail the batch
+    bad = ix.feed_batch([{"id": "x", "fields": {"marqo__embeddings_title": {"0": [1.0] * 8}}},
+                         _doc("ok", {}, {"title": (["t"], unit(1))})], "s1")
+    assert bad.errors and bad.responses[0].status == 400 and bad.responses[1].status == 200
+    ix.close()

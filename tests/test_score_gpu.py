@@ -94,6 +94,27 @@ def test_max_over_chunks_and_delete(gpu_required, score_oracle):
     _check(store, score_oracle, q, corpus, 10, "prenormalized-angular", dd)
 
 
+@pytest.mark.parametrize("k", [11, 16, 50, 200])
+def test_large_k_multi_round(gpu_required, score_oracle, k):
+    """k beyond the single-pass limit (Marqo allows limit <= 1000): multi-round scan, same exact order."""
+    from marqo_b200.engine import RowStore
+    rng = np.random.default_rng(k)
+    n, d = 6000, 128
+    corpus = _unit_rows(rng, n, d)
+    corpus[100:140] = corpus[5]                                   # a run of exact ties across the round boundary
+    doc_of_row = (np.arange(n) // 2).astype(np.int32)            # 2 chunks per doc
+    q = _unit_rows(rng, 7, d)
+    q[0] = corpus[5]
+    store = RowStore(d)
+    store.add(corpus, doc_of_row)
+    _check(store, score_oracle, q, corpus, k, "prenormalized-angular", doc_of_row)
+    small = RowStore(d)
+    small.add(corpus[:30])                                        # fewer documents than k
+    doc, row, score = small.search(q[:2], k)
+    assert (doc[:, :30] >= 0).all() and (doc[:, 30:] == -1).all()
+    _check(small, score_oracle, q[:2], corpus[:30], k, "prenormalized-angular")
+
+
 def test_empty_and_small(gpu_required):
     from marqo_b200.engine import RowStore
     store = RowStore(64)
