@@ -28,10 +28,109 @@ constexpr uint32_t SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTE
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t S_COL = 0, O_COL = 128;
 
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Query rows that do not fill a 128-row tile (e.g. row 256 of a 257-token ViT sequence): one warp per
+// (batch, head, row); lanes stride over the keys with a private online softmax, then merge across lanes.
+template <int MASK>
+__global__ void __launch_bounds__(128)
+attention_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int W, int H,
+                           int row_lo, const int32_t* __restrict__ kv_len, float scale_log2e, int total) {
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (wid >= total) return;
+    const int nrows = S - row_lo;
+    const int qrow = row_lo + wid % nrows;
+    const int h = (wid / nrows) % H;
+    const int b = wid / (nrows * H);
+    const size_t ld = (size_t)3 * W;
+    const __nv_bfloat16* seq = qkv + (size_t)b * S * ld;
+    int len = S;
+    if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[b], 0));
+    if (MASK == MASK_CAUSAL) len = min(len, qrow + 1);
+    float q[HD];
+    {
+        const uint4* qp = reinterpret_cast<const uint4*>(seq + (size_t)qrow * ld + h * HD);
+#pragma unroll
+        for (int u = 0; u < HD / 8; ++u) {
+            const uint4 t4 = __ldg(qp + u);
+            const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+                q[8 * u + 2 * e] = f2.x * scale_log2e;
+                q[8 * u + 2 * e + 1] = f2.y * scale_log2e;
+            }
+        }
+    }
+    float m = -INFINITY, l = 0.f;
+    float o[HD];
+#pragma unroll
+    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    for (int key = lane; key < len; key += 32) {
+        const uint4* kp = reinterpret_cast<const uint4*>(seq + (size_t)key * ld + W + h * HD);
+        const uint4* vp = reinterpret_cast<const uint4*>(seq + (size_t)key * ld + 2 * W + h * HD);
+        float sc = 0.f;
+#pragma unroll
+        for (int u = 0; u < HD / 8; ++u) {
+            const uint4 k4 = __ldg(kp + u);
+            const uint32_t w4[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+                sc = fmaf(q[8 * u + 2 * e], f2.x, sc);
+                sc = fmaf(q[8 * u + 2 * e + 1], f2.y, sc);
+            }
+        }
+        const float m_new = fmaxf(m, sc);
+        const float alpha = ex2(m - m_new);
+        const float pe = ex2(sc - m_new);
+        const float pb = __bfloat162float(__float2bfloat16_rn(pe));  // same P rounding as the tensor-core path
+        l = l * alpha + pe;
+        m = m_new;
+#pragma unroll
+        for (int u = 0; u < HD / 8; ++u) {
+            const uint4 v4 = __ldg(vp + u);
+            const uint32_t w4[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+                o[8 * u + 2 * e] = fmaf(o[8 * u + 2 * e], alpha, pb * f2.x);
+                o[8 * u + 2 * e + 1] = fmaf(o[8 * u + 2 * e + 1], alpha, pb * f2.y);
+            }
+        }
+    }
+    // merge the 32 partial softmaxes
+    float mg = m;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, off));
+    const float corr = m == -INFINITY ? 0.f : ex2(m - mg);
+    l *= corr;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat16* dst = out + ((size_t)b * S + qrow) * W + h * HD;
+#pragma unroll
+    for (int i = 0; i < HD; ++i) {
+        float v = o[i] * corr;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == (i & 31)) dst[i] = __float2bfloat16_rn(v * inv);
+    }
+}
+
 template <int MASK>
 __global__ void __launch_bounds__(THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __restrict__ out, int S, int W,
-                    const int32_t* __restrict__ kv_len, float scale_log2e) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ qkv,
+                    __nv_bfloat16* __restrict__ out, int S, int W, const int32_t* __restrict__ kv_len, float scale_log2e,
+                    int s_main) {
+    // Keys [0, s_main) go through the tensor cores in blocks of 128; the few keys [s_main, S) of a sequence length
+    // such as 257 = 2 * 128 + 1 (ViT class token) are folded in on the CUDA cores in the epilogue instead of paying
+    // for a whole extra 128-wide block.
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;
     uint8_t* sKV = sQ + Q_BYTES;                       // stage s: K at sKV + s*32K, V at +16K
@@ -53,8 +152,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __r
 
     int len = S;
     if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[b], 0));
-    int kend = len;
-    if (MASK == MASK_CAUSAL) kend = min(len, q0 + BQ);
+    int kend = min(len, s_main);
+    if (MASK == MASK_CAUSAL) kend = min(kend, q0 + BQ);
     const int nkb = (kend + BKV - 1) / BKV;
     const int row_base = b * S;  // first row of this sequence in the packed [B*S, 3W] matrix
 
@@ -142,8 +241,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __r
             const uint32_t par = j & 1;
             ptx::mbar_wait(s_full, par);
             ptx::tc_fence_after();
-            int limit = len - j * BKV;  // keys with index >= limit are masked
+            int limit = kend - j * BKV;  // keys with block-local index >= limit are masked
             if (MASK == MASK_CAUSAL) limit = min(limit, qrow - j * BKV + 1);
+            const bool full = limit >= BKV;
             // pass 1: row maximum of this block
             float mx = -INFINITY;
 #pragma unroll 1
@@ -151,14 +251,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __r
                 uint32_t v[32];
                 ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, v);
                 ptx::tmem_ld_wait();
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c * 32 + i < limit) mx = fmaxf(mx, __uint_as_float(v[i]));
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i < limit) mx = fmaxf(mx, __uint_as_float(v[i]));
+                }
             }
             mx *= scale_log2e;  // scale > 0: max commutes with the scaling
             const float m_new = fmaxf(m_run, mx);
             const float m_safe = m_new == -INFINITY ? 0.f : m_new;
-            const float alpha = exp2f(m_run - m_safe);  // 0 on the first block
+            const float alpha = ex2(m_run - m_safe);  // 0 on the first block
             if (j > 0) ptx::mbar_wait(pv_done, par ^ 1);  // P buffer and O accumulator are free again
             // pass 2: p = exp2(s - m), row sum, bf16 P into the K-major 128B-swizzled A-operand layout
             float lsum = 0.f;
@@ -168,13 +273,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __r
                 ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, v);
                 ptx::tmem_ld_wait();
                 uint32_t pk[16];
+                if (full) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = c * 32 + i < limit ? exp2f(__uint_as_float(v[i]) * scale_log2e - m_safe) : 0.f;
-                    const float p1 = c * 32 + i + 1 < limit ? exp2f(__uint_as_float(v[i + 1]) * scale_log2e - m_safe) : 0.f;
-                    lsum += p0 + p1;
-                    __nv_bfloat162 t2 = __floats2bfloat162_rn(p0, p1);
-                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = ex2(fmaf(__uint_as_float(v[i]), scale_log2e, -m_safe));
+                        const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2e, -m_safe));
+                        lsum += p0 + p1;
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float p0 = c * 32 + i < limit ? ex2(fmaf(__uint_as_float(v[i]), scale_log2e, -m_safe)) : 0.f;
+                        const float p1 =
+                            c * 32 + i + 1 < limit ? ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2e, -m_safe)) : 0.f;
+                        lsum += p0 + p1;
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(p0, p1);
+                        pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+                    }
                 }
                 // keys c*32 .. c*32+31 -> chunk (c >> 1), 16-byte units (c & 1) * 4 .. +3 of row r
                 uint8_t* rowp = sP + (size_t)(c >> 1) * (BQ * 128) + (size_t)r * 128;
@@ -209,33 +326,86 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, __nv_bfloat16* __r
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(p_full);
         }
-        // ------------------------------------------------------------------ epilogue: O / l -> bf16 -> global
+        // ------------------------------------------------------------------ epilogue: (+ tail keys) O / l -> bf16
+        float o[HD];
         if (nkb > 0) {
             ptx::mbar_wait(pv_done, (nkb - 1) & 1);
             ptx::tc_fence_after();
-        }
-        const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-        __nv_bfloat16* dst = out + ((size_t)row_base + qrow) * W + h * HD;
-#pragma unroll 1
-        for (int c = 0; c < HD / 32; ++c) {
-            uint32_t v[32];
-            if (nkb > 0) {
-                ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + c * 32, v);
-                ptx::tmem_ld_wait();
-            } else {
+            uint32_t v0[32], v1[32];
+            ptx::tmem_ld_32x32b_x32(lane_addr + O_COL, v0);
+            ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + 32, v1);
+            ptx::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = 0u;
+            for (int i = 0; i < 32; ++i) {
+                o[i] = __uint_as_float(v0[i]);
+                o[32 + i] = __uint_as_float(v1[i]);
             }
-            if (qrow < S) {
-                uint32_t pk[16];
+        } else {
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    __nv_bfloat162 t2 = __floats2bfloat162_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
-                    pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
+            for (int i = 0; i < HD; ++i) o[i] = 0.f;
+        }
+        if (qrow < S) {
+            const int tail_end = MASK == MASK_CAUSAL ? min(len, qrow + 1) : len;
+            if (s_main < tail_end) {
+                // tail keys on the CUDA cores: s = q . k, online-softmax update of (m, l, o) with p * v
+                const size_t ld = (size_t)3 * W;
+                uint32_t qreg[HD / 2];
+                const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)row_base + qrow) * ld + h * HD);
+#pragma unroll
+                for (int u = 0; u < HD / 8; ++u) {
+                    const uint4 t4 = qp[u];
+                    qreg[4 * u] = t4.x;
+                    qreg[4 * u + 1] = t4.y;
+                    qreg[4 * u + 2] = t4.z;
+                    qreg[4 * u + 3] = t4.w;
                 }
-                uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+                for (int key = s_main; key < tail_end; ++key) {
+                    const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)row_base + key) * ld + W + h * HD);
+                    const uint4* vp = reinterpret_cast<const uint4*>(qkv + ((size_t)row_base + key) * ld + 2 * W + h * HD);
+                    float sdot = 0.f;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) d4[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                    for (int u = 0; u < HD / 8; ++u) {
+                        const uint4 k4 = __ldg(kp + u);
+                        const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 qa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qreg[4 * u + e]));
+                            const float2 ka = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk[e]));
+                            sdot = fmaf(qa.x, ka.x, sdot);
+                            sdot = fmaf(qa.y, ka.y, sdot);
+                        }
+                    }
+                    const float sc = sdot * scale_log2e;
+                    const float m_new = fmaxf(m_run, sc);
+                    const float alpha = ex2(m_run - m_new);
+                    // the tensor-core path rounds P to bf16 before the PV product: do the same here
+                    const float pexp = __bfloat162float(__float2bfloat16_rn(ex2(sc - m_new)));
+                    l_run = l_run * alpha + ex2(sc - m_new);
+                    m_run = m_new;
+#pragma unroll
+                    for (int u = 0; u < HD / 8; ++u) {
+                        const uint4 v4 = __ldg(vp + u);
+                        const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 va = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[e]));
+                            o[8 * u + 2 * e] = fmaf(o[8 * u + 2 * e], alpha, pexp * va.x);
+                            o[8 * u + 2 * e + 1] = fmaf(o[8 * u + 2 * e + 1], alpha, pexp * va.y);
+                        }
+                    }
+                }
+            }
+            const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+            uint4* d4 = reinterpret_cast<uint4*>(out + ((size_t)row_base + qrow) * W + h * HD);
+#pragma unroll
+            for (int u = 0; u < HD / 8; ++u) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    __nv_bfloat162 t2 = __floats2bfloat162_rn(o[8 * u + 2 * e] * inv, o[8 * u + 2 * e + 1] * inv);
+                    pk[e] = *reinterpret_cast<uint32_t*>(&t2);
+                }
+                d4[u] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
         }
     }
@@ -268,21 +438,37 @@ void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W
     // rows past the end of the matrix are zero-filled, rows of the next sequence are masked by key index
     CUtensorMap tmap = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,
                                     (uint64_t)3 * W * 2, tc::HD, tc::BQ, CU_TENSOR_MAP_SWIZZLE_128B);
-    const dim3 grid((S + tc::BQ - 1) / tc::BQ, H, B);
+    // A short remainder (S = 257, 129, ...) is not worth a 128-wide tile in either dimension.
+    constexpr int TAIL_MAX = 8;
+    const int rem = S % tc::BQ;
+    const bool tail = S >= tc::BQ && rem > 0 && rem <= TAIL_MAX;
+    const int s_main = tail ? S - rem : S;                       // keys handled by the tensor cores
+    const int q_blocks = tail ? S / tc::BQ : (S + tc::BQ - 1) / tc::BQ;
+    const dim3 grid(q_blocks, H, B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;
+    const int tail_total = tail ? B * H * rem : 0;
     switch (mask) {
         case MASK_NONE:
-            tc::attention_tc_kernel<MASK_NONE><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, out, S, W, kv_len,
-                                                                                             scale_log2e);
+            tc::attention_tc_kernel<MASK_NONE><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, kv_len,
+                                                                                             scale_log2e, s_main);
+            if (tail)
+                tc::attention_tail_rows_kernel<MASK_NONE><<<(tail_total + 3) / 4, 128, 0, stream>>>(
+                    qkv, out, S, W, H, s_main, kv_len, scale_log2e, tail_total);
             break;
         case MASK_CAUSAL:
-            tc::attention_tc_kernel<MASK_CAUSAL><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, out, S, W, kv_len,
-                                                                                               scale_log2e);
+            tc::attention_tc_kernel<MASK_CAUSAL><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, kv_len,
+                                                                                               scale_log2e, s_main);
+            if (tail)
+                tc::attention_tail_rows_kernel<MASK_CAUSAL><<<(tail_total + 3) / 4, 128, 0, stream>>>(
+                    qkv, out, S, W, H, s_main, kv_len, scale_log2e, tail_total);
             break;
         case MASK_KEYLEN:
             if (!kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
-            tc::attention_tc_kernel<MASK_KEYLEN><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, out, S, W, kv_len,
-                                                                                               scale_log2e);
+            tc::attention_tc_kernel<MASK_KEYLEN><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, kv_len,
+                                                                                               scale_log2e, s_main);
+            if (tail)
+                tc::attention_tail_rows_kernel<MASK_KEYLEN><<<(tail_total + 3) / 4, 128, 0, stream>>>(
+                    qkv, out, S, W, H, s_main, kv_len, scale_log2e, tail_total);
             break;
         default:
             fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);

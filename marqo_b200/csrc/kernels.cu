@@ -257,48 +257,94 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
     return t;
 }
 
+// CLIP head: 8 images per CTA so that every element of the fp32 projection matrix read from L2 feeds 8 FMAs.
+constexpr int HEAD_IMGS = 8;
+
 __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict__ x, int S, const int32_t* __restrict__ row_in_seq,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float eps, const float* __restrict__ proj, int w, int E,
+                                                        float eps, const float* __restrict__ proj, int n, int w, int E,
                                                         int normalize, float* __restrict__ out) {
-    extern __shared__ float sh[];  // [w] pooled + [E] projected
-    __shared__ float red[8];
-    float* pooled = sh;
-    float* res = sh + w;
-    const int b = blockIdx.x;
-    const int r = row_in_seq ? row_in_seq[b] : 0;
-    const float* src = x + ((long long)b * S + r) * w;
-    float s = 0.f;
-    for (int i = threadIdx.x; i < w; i += 256) {
-        const float v = src[i];
-        pooled[i] = v;
-        s += v;
+    extern __shared__ float sh[];          // pooledT [w][8]  +  res [8][E]
+    __shared__ float red[8][HEAD_IMGS];
+    float* pooledT = sh;
+    float* res = sh + (size_t)w * HEAD_IMGS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b0 = blockIdx.x * HEAD_IMGS;
+    {   // LayerNorm: warp k normalises image b0 + k (two-pass, like layernorm_kernel)
+        const int b = b0 + warp;
+        if (b < n) {
+            const int r = row_in_seq ? row_in_seq[b] : 0;
+            const float* src = x + ((long long)b * S + r) * w;
+            float s = 0.f;
+            for (int i = lane; i < w; i += 32) s += src[i];
+            const float mean = warp_sum(s) / (float)w;
+            float q = 0.f;
+            for (int i = lane; i < w; i += 32) {
+                const float d = src[i] - mean;
+                q += d * d;
+            }
+            const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)w + eps);
+            for (int i = lane; i < w; i += 32) pooledT[i * HEAD_IMGS + warp] = (src[i] - mean) * rstd * gamma[i] + beta[i];
+        } else {
+            for (int i = lane; i < w; i += 32) pooledT[i * HEAD_IMGS + warp] = 0.f;
+        }
     }
-    const float mean = block_sum_256(s, red) / (float)w;
-    float q = 0.f;
-    for (int i = threadIdx.x; i < w; i += 256) {
-        const float d = pooled[i] - mean;
-        q += d * d;
-    }
-    const float rstd = 1.0f / sqrtf(block_sum_256(q, red) / (float)w + eps);
-    for (int i = threadIdx.x; i < w; i += 256) pooled[i] = (pooled[i] - mean) * rstd * gamma[i] + beta[i];
     __syncthreads();
-    float ss = 0.f;
+    float ss[HEAD_IMGS];
+#pragma unroll
+    for (int k = 0; k < HEAD_IMGS; ++k) ss[k] = 0.f;
     for (int e = threadIdx.x; e < E; e += 256) {
-        float acc = 0.f;
-        for (int i = 0; i < w; ++i) acc = fmaf(pooled[i], __ldg(proj + (long long)i * E + e), acc);
-        res[e] = acc;
-        ss += acc * acc;
+        float acc[HEAD_IMGS];
+#pragma unroll
+        for (int k = 0; k < HEAD_IMGS; ++k) acc[k] = 0.f;
+        for (int i = 0; i < w; ++i) {
+            const float pj = __ldg(proj + (long long)i * E + e);
+            const float4 a = *reinterpret_cast<const float4*>(pooledT + i * HEAD_IMGS);
+            const float4 c = *reinterpret_cast<const float4*>(pooledT + i * HEAD_IMGS + 4);
+            acc[0] = fmaf(a.x, pj, acc[0]);
+            acc[1] = fmaf(a.y, pj, acc[1]);
+            acc[2] = fmaf(a.z, pj, acc[2]);
+            acc[3] = fmaf(a.w, pj, acc[3]);
+            acc[4] = fmaf(c.x, pj, acc[4]);
+            acc[5] = fmaf(c.y, pj, acc[5]);
+            acc[6] = fmaf(c.z, pj, acc[6]);
+            acc[7] = fmaf(c.w, pj, acc[7]);
+        }
+#pragma unroll
+        for (int k = 0; k < HEAD_IMGS; ++k) {
+            res[k * E + e] = acc[k];
+            ss[k] += acc[k] * acc[k];
+        }
     }
-    const float nrm = sqrtf(block_sum_256(ss, red));
-    for (int e = threadIdx.x; e < E; e += 256) out[(long long)b * E + e] = normalize ? res[e] / nrm : res[e];
+#pragma unroll
+    for (int k = 0; k < HEAD_IMGS; ++k) {
+        const float v = warp_sum(ss[k]);
+        if (lane == 0) red[warp][k] = v;
+    }
+    __syncthreads();
+    for (int k = 0; k < HEAD_IMGS; ++k) {
+        const int b = b0 + k;
+        if (b >= n) break;
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += red[i][k];
+        const float nrm = sqrtf(t);
+        for (int e = threadIdx.x; e < E; e += 256) out[(long long)b * E + e] = normalize ? res[k * E + e] / nrm : res[k * E + e];
+    }
 }
 
 void clip_head(const float* x, int S, const int32_t* row_in_seq, const float* gamma, const float* beta, float eps,
                const float* proj, int n, int w, int E, int normalize, float* out, cudaStream_t s) {
     if (n <= 0) return;
-    clip_head_kernel<<<n, 256, (size_t)(w + E) * sizeof(float), s>>>(x, S, row_in_seq, gamma, beta, eps, proj, w, E,
-                                                                    normalize, out);
+    const size_t smem = ((size_t)w * HEAD_IMGS + (size_t)HEAD_IMGS * E) * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        MB_CUDA(cudaFuncSetAttribute(clip_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    if (smem > 160 * 1024) fail(B200_ERR_UNSUPPORTED, "clip_head: width %d / embed %d too large", w, E);
+    clip_head_kernel<<<(n + HEAD_IMGS - 1) / HEAD_IMGS, 256, smem, s>>>(x, S, row_in_seq, gamma, beta, eps, proj, n, w, E,
+                                                                        normalize, out);
     MB_CUDA(cudaGetLastError());
 }
 

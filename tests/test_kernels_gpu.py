@@ -47,6 +47,8 @@ def test_gemm_epilogues(gpu_required, act):
 
 @pytest.mark.parametrize("B,S,H,mask", [
     (2, 50, 12, 0), (3, 257, 4, 0), (2, 77, 8, 1), (4, 128, 12, 2), (2, 512, 2, 2), (1, 1, 2, 0), (2, 64, 2, 1), (1, 65, 2, 1),
+    (2, 129, 2, 0), (2, 136, 2, 2), (2, 137, 2, 0), (3, 385, 2, 2), (2, 129, 2, 1), (2, 260, 2, 1), (1, 300, 2, 1), (2, 256, 4, 0),
+    (1, 1025, 2, 0),
 ])
 def test_attention_matches_torch(gpu_required, B, S, H, mask):
     from marqo_b200.engine import debug_attention

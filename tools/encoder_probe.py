@@ -52,3 +52,9 @@ ms = sorted(r[0] for r in res[1:])
 med = ms[len(ms) // 2]
 print(json.dumps({"model": name, "mode": mode, "B": B, "S": S, "ms_med": med, "ms_min": ms[0], "items_per_s": B / med * 1e3,
                   "TFLOPs": flops / med / 1e9, "launches": res[-1][1], "finite": bool(torch.isfinite(out).all())}))
+enc.set_profiling(True)
+for i in range(3):
+    run()
+torch.cuda.synchronize()
+pr = enc.profile()
+print(json.dumps({k: (v / 3 if k.endswith("_ms") else v // 3) for k, v in pr.items()}))
