@@ -1,5 +1,7 @@
-// Multi-head attention over packed QKV (head_dim 64): flash-style online softmax, bf16 tensor-core MMAs
-// (mma.sync m16n8k16 — the legacy warp-level path; attention is ~4% of the encoder FLOPs, the GEMMs are tcgen05).
+// Multi-head attention over packed QKV (head_dim 64), flash-style online softmax in fp32.
+//   S >= 128: tcgen05 / TMEM kernel (attention_tc.cu) — 128 x 128 tiles, TMA-fed, thread-per-row softmax.
+//   S <  128: 64-row warp-level kernel (attention.cu, mma.sync m16n8k16) — short sequences would leave most of a
+//             128-wide tcgen05 tile masked.
 #pragma once
 #include "common.cuh"
 

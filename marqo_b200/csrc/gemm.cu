@@ -25,9 +25,14 @@ struct Cfg {
     static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN < 32 ? 32 : ACC_STAGES * BN;
 };
 
+// Clusters of CLUSTER CTAs work on vertically adjacent tiles (same n, m and m + 128) in lock step: each CTA fetches
+// half of the shared W tile and multicasts it to both, so the L2 -> SM traffic per tile drops from A + W to A + W/2.
+constexpr int CLUSTER = 2;
+
 struct Params {
     int M, N, K;
-    int tiles_m, tiles_n;
+    int tiles_m, tiles_n;   // tiles_m counts 128-row blocks
+    int super_m;            // ceil(tiles_m / CLUSTER)
     Epilogue ep;
 };
 
@@ -85,14 +90,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int kblocks = p.K / BK;
-    const int num_tiles = p.tiles_m * p.tiles_n;
+    const uint32_t crank = ptx::cluster_ctarank();
+    const int cluster_id = blockIdx.x / CLUSTER;
+    const int num_clusters = gridDim.x / CLUSTER;
+    const int num_super = p.super_m * p.tiles_n;   // (pair of m-blocks) x n-block units, one per cluster step
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
         for (int i = 0; i < C::STAGES; ++i) {
             ptx::mbar_init(&full[i], 1);
-            ptx::mbar_init(&empty[i], 1);
+            ptx::mbar_init(&empty[i], CLUSTER);   // released by the MMA warps of both CTAs (both read the shared W)
         }
         for (int i = 0; i < ACC_STAGES; ++i) {
             ptx::mbar_init(&tfull[i], 1);
@@ -106,6 +114,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();   // the peer's barriers are initialised before any multicast can land there
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -113,16 +122,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t / p.tiles_n) * BM;
+            for (int t = cluster_id; t < num_super; t += num_clusters) {
+                const int m0 = ((t / p.tiles_n) * CLUSTER + (int)crank) * BM;
                 const int n0 = (t % p.tiles_n) * BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
                     ptx::tma_load_2d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, &full[stage], kb * BK, m0,
                                      ptx::kEvictNormal);
-                    ptx::tma_load_2d(smem_b + (size_t)stage * C::B_STAGE_BYTES, &tmap_b, &full[stage], kb * BK, n0,
-                                     ptx::kEvictLast);
+                    // my half of the W tile, delivered to both CTAs of the cluster
+                    ptx::tma_load_2d_multicast(
+                        smem_b + (size_t)stage * C::B_STAGE_BYTES + (size_t)crank * (C::B_STAGE_BYTES / CLUSTER), &tmap_b,
+                        &full[stage], kb * BK, n0 + (int)crank * (BN / CLUSTER), (uint16_t)((1u << CLUSTER) - 1),
+                        ptx::kEvictLast);
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -134,7 +146,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         constexpr uint32_t idesc = ptx::make_idesc_f16(1 /*bf16*/, BM, BN);
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = cluster_id; t < num_super; t += num_clusters) {
             ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
             ptx::tc_fence_after();
             for (int kb = 0; kb < kblocks; ++kb) {
@@ -147,7 +159,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     for (int k = 0; k < BK / UMMA_K; ++k)
                         ptx::umma_f16(tmem_base + acc * BN, ptx::make_desc_k_sw128(a_base + k * UMMA_K * 2),
                                       ptx::make_desc_k_sw128(b_base + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit(&empty[stage]);
+                    ptx::umma_commit_multicast(&empty[stage], (uint16_t)((1u << CLUSTER) - 1));
                     if (kb == kblocks - 1) ptx::umma_commit(&tfull[acc]);
                 }
                 __syncwarp();
@@ -173,8 +185,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const Epilogue& ep = p.ep;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-            const int m0 = (t / p.tiles_n) * BM;
+        for (int t = cluster_id; t < num_super; t += num_clusters) {
+            const int m0 = ((t / p.tiles_n) * CLUSTER + (int)crank) * BM;
             const int nt0 = (t % p.tiles_n) * BN + half * HALF_COLS;
             const int row = m0 + sp * 32 + lane;
             const bool row_ok = row < p.M;
@@ -189,10 +201,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 // pull the residual segment this thread will need for its NEXT tile towards L2 (one tile ahead: the
                 // loads below then hit L2 instead of paying HBM latency inside the serial chunk loop); the very first
                 // tile prefetches for itself.
-                for (int pass = (t == (int)blockIdx.x ? 0 : 1); pass < 2; ++pass) {
-                    const int tn = t + pass * gridDim.x;
-                    if (tn >= num_tiles) break;
-                    const int prow = (tn / p.tiles_n) * BM + sp * 32 + lane;
+                for (int pass = (t == cluster_id ? 0 : 1); pass < 2; ++pass) {
+                    const int tn = t + pass * num_clusters;
+                    if (tn >= num_super) break;
+                    const int prow = ((tn / p.tiles_n) * CLUSTER + (int)crank) * BM + sp * 32 + lane;
                     const int pn0 = (tn % p.tiles_n) * BN + half * HALF_COLS;
                     if (prow < p.M) {
                         const char* r = reinterpret_cast<const char*>(ep.residual + (size_t)prow * ep.ldr + pn0);
@@ -284,6 +296,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();   // nobody exits while the peer may still multicast into / arrive on this CTA's smem
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -311,14 +324,28 @@ static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     p.K = K;
     p.tiles_m = (M + BM - 1) / BM;
     p.tiles_n = (N + BN - 1) / BN;
+    p.super_m = (p.tiles_m + CLUSTER - 1) / CLUSTER;
     p.ep = ep;
     CUtensorMap ta = make_tmap_2d(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK,
                                   BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    // each CTA of a cluster fetches BN / CLUSTER rows of the W tile
     CUtensorMap tb = make_tmap_2d(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, BK,
-                                  BN, CU_TENSOR_MAP_SWIZZLE_128B);
-    const int grid = std::min(p.tiles_m * p.tiles_n, sms);
-    gemm_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM_BYTES, stream>>>(ta, tb, p);
-    MB_CUDA(cudaGetLastError());
+                                  BN / CLUSTER, CU_TENSOR_MAP_SWIZZLE_128B);
+    const int max_clusters = sms / CLUSTER;
+    const int clusters = std::min(p.super_m * p.tiles_n, max_clusters);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * CLUSTER);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MB_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN>, ta, tb, p));
 }
 
 void launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const Epilogue& ep, int sms,
