@@ -18,15 +18,17 @@ constexpr int SMEM_LIMIT = 232448;
 
 template <int BN>
 struct Cfg {
-    static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
+    static constexpr uint32_t B_STAGE_BYTES = (BN / 2) * BK * 2;   // each CTA of the pair holds half of the W tile
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES > 8 ? 8 : (SMEM_LIMIT - 2048) / STAGE_BYTES;
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
     static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN < 32 ? 32 : ACC_STAGES * BN;
 };
 
-// Clusters of CLUSTER CTAs work on vertically adjacent tiles (same n, m and m + 128) in lock step: each CTA fetches
-// half of the shared W tile and multicasts it to both, so the L2 -> SM traffic per tile drops from A + W to A + W/2.
+// CTA pairs (cta_group::2): one tcgen05.mma spans both SMs of a pair — a 256 x BN tile, 128 rows of A and BN/2 rows
+// of W in each SM's shared memory.  Per SM and k-block the tensor core reads 16 KB instead of 24 KB and TMA writes
+// 32 KB instead of 48 KB, which takes the single-CTA kernel off its shared-memory-bandwidth ceiling (ncu: the MMA
+// warp never waited for data, yet the tensor pipe stalled at ~70 %).
 constexpr int CLUSTER = 2;
 
 struct Params {
@@ -99,18 +101,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
         for (int i = 0; i < C::STAGES; ++i) {
-            ptx::mbar_init(&full[i], 1);
-            ptx::mbar_init(&empty[i], CLUSTER);   // released by the MMA warps of both CTAs (both read the shared W)
+            ptx::mbar_init(&full[i], CLUSTER);    // leader's copy is used: its own arrive.expect_tx + the peer's arrive
+            ptx::mbar_init(&empty[i], 1);         // one multicast tcgen05.commit per use, in each CTA
         }
         for (int i = 0; i < ACC_STAGES; ++i) {
             ptx::mbar_init(&tfull[i], 1);
-            ptx::mbar_init(&tempty[i], EPI_WARPS);
+            ptx::mbar_init(&tempty[i], CLUSTER * EPI_WARPS);   // leader's copy: epilogue warps of both CTAs
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 1) {
-        ptx::tmem_alloc(tmem_slot, C::TMEM_COLS);
-        ptx::tmem_relinquish();
+    if (warp == 1) {   // executed by both CTAs of the pair
+        ptx::tmem_alloc_2sm<C::TMEM_COLS>(tmem_slot);
+        ptx::tmem_relinquish_2sm();
     }
     ptx::tc_fence_before();
     __syncthreads();
@@ -127,14 +129,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 const int n0 = (t % p.tiles_n) * BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
-                    ptx::tma_load_2d(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, &full[stage], kb * BK, m0,
-                                     ptx::kEvictNormal);
-                    // my half of the W tile, delivered to both CTAs of the cluster
-                    ptx::tma_load_2d_multicast(
-                        smem_b + (size_t)stage * C::B_STAGE_BYTES + (size_t)crank * (C::B_STAGE_BYTES / CLUSTER), &tmap_b,
-                        &full[stage], kb * BK, n0 + (int)crank * (BN / CLUSTER), (uint16_t)((1u << CLUSTER) - 1),
-                        ptx::kEvictLast);
+                    // completion of BOTH CTAs' loads is tracked by the leader's full barrier
+                    const uint32_t leader_full = ptx::mapa_u32(ptx::smem_u32(&full[stage]), 0);
+                    if (crank == 0)
+                        ptx::mbar_arrive_expect_tx(&full[stage], CLUSTER * C::STAGE_BYTES);
+                    else
+                        ptx::mbar_arrive_cluster(leader_full);
+                    ptx::tma_load_2d_2sm(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, leader_full, kb * BK, m0,
+                                         ptx::kEvictNormal);
+                    ptx::tma_load_2d_2sm(smem_b + (size_t)stage * C::B_STAGE_BYTES, &tmap_b, leader_full, kb * BK,
+                                         n0 + (int)crank * (BN / CLUSTER), ptx::kEvictLast);
                     if (++stage == C::STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -142,8 +146,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 }
             }
         }
-    } else if (warp == 1) {
-        constexpr uint32_t idesc = ptx::make_idesc_f16(1 /*bf16*/, BM, BN);
+    } else if (warp == 1 && crank == 0) {
+        constexpr uint32_t idesc = ptx::make_idesc_f16(1 /*bf16*/, CLUSTER * BM, BN);   // M = 256 across the pair
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         for (int t = cluster_id; t < num_super; t += num_clusters) {
@@ -157,10 +161,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     const uint32_t b_base = ptx::smem_u32(smem_b + (size_t)stage * C::B_STAGE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        ptx::umma_f16(tmem_base + acc * BN, ptx::make_desc_k_sw128(a_base + k * UMMA_K * 2),
-                                      ptx::make_desc_k_sw128(b_base + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                    ptx::umma_commit_multicast(&empty[stage], (uint16_t)((1u << CLUSTER) - 1));
-                    if (kb == kblocks - 1) ptx::umma_commit(&tfull[acc]);
+                        ptx::umma_f16_2sm(tmem_base + acc * BN, ptx::make_desc_k_sw128(a_base + k * UMMA_K * 2),
+                                          ptx::make_desc_k_sw128(b_base + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    // both CTAs' producers get their stage back; both CTAs' epilogues get the finished accumulator
+                    ptx::umma_commit_2sm(&empty[stage], (uint16_t)((1u << CLUSTER) - 1));
+                    if (kb == kblocks - 1) ptx::umma_commit_2sm(&tfull[acc], (uint16_t)((1u << CLUSTER) - 1));
                 }
                 __syncwarp();
                 if (++stage == C::STAGES) {
@@ -173,7 +178,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
-    } else {
+    } else if (warp >= 2) {
         // ---------------------------------------------------------------- epilogue (TMEM -> regs -> global)
         // A warp may only read the TMEM lanes of sub-partition (warp % 4); the two warps that share a sub-partition
         // split the tile's columns in halves, so 8 warps drain one 128 x BN accumulator.
@@ -227,7 +232,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     // this warp's share of the accumulator is in registers: hand it back to the MMA warp
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+                    if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty[acc]), 0));
                 }
                 const int n0 = nt0 + c * 32;
                 if (has_cols && row_ok && n0 < p.N) {
@@ -299,7 +304,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     ptx::cluster_sync();   // nobody exits while the peer may still multicast into / arrive on this CTA's smem
     if (warp == 1) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+        ptx::tmem_dealloc_2sm<C::TMEM_COLS>(tmem_base);
     }
 }
 
@@ -328,7 +333,7 @@ static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     p.ep = ep;
     CUtensorMap ta = make_tmap_2d(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK,
                                   BM, CU_TENSOR_MAP_SWIZZLE_128B);
-    // each CTA of a cluster fetches BN / CLUSTER rows of the W tile
+    // each CTA of the pair fetches (and keeps) BN / 2 rows of the W tile
     CUtensorMap tb = make_tmap_2d(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, BK,
                                   BN / CLUSTER, CU_TENSOR_MAP_SWIZZLE_128B);
     const int max_clusters = sms / CLUSTER;

@@ -265,4 +265,55 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ct
                  "h"(cta_mask)
                  : "memory");
 }
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+    return r;
+}
+// arrive on an mbarrier that lives in another CTA of the cluster (address from mapa_u32)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on an mbarrier of EITHER CTA of the pair (cluster address)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr,
+                                                int32_t c0, int32_t c1, uint64_t cache_hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1),
+        "l"(cache_hint)
+        : "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(NCOLS)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t NCOLS>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// one MMA spanning both SMs of the pair: M = 256 (128 rows per CTA); each CTA's smem supplies its 128 rows of A and
+// its half of the N rows of B
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
 }  // namespace ptx
