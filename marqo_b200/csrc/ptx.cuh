@@ -273,7 +273,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 }
 // arrive on an mbarrier that lives in another CTA of the cluster (address from mapa_u32)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // plain (cta-scope release) form: a cluster-scope release costs ~1000 cycles per arrive (measured: it serialised
+    // the peer CTA's TMA issue); the data hand-off is tracked by complete_tx / tcgen05 fences, not by this arrive
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load whose completion is signalled on an mbarrier of EITHER CTA of the pair (cluster address)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tmap, uint32_t bar_cluster_addr,
