@@ -35,12 +35,17 @@ __device__ __forceinline__ float ex2(float x) {
 }
 
 // Query rows that do not fill a 128-row tile (e.g. row 256 of a 257-token ViT sequence): one warp per
-// (batch, head, row); lanes stride over the keys with a private online softmax, then merge across lanes.
+// (batch, head, row).  Phase 1: lanes stride over the keys and compute the scores into shared memory; phase 2: lanes
+// stride over the 64 output dims and accumulate p_j * V[j] with coalesced 128-byte row reads.
+constexpr int TAIL_S_MAX = 1024;
+
 template <int MASK>
 __global__ void __launch_bounds__(128)
 attention_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int W, int H,
                            int row_lo, const int32_t* __restrict__ kv_len, float scale_log2e, int total) {
-    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);
+    __shared__ float s_sc[4][TAIL_S_MAX];
+    const int wib = threadIdx.x >> 5;
+    const int wid = blockIdx.x * 4 + wib;
     const int lane = threadIdx.x & 31;
     if (wid >= total) return;
     const int nrows = S - row_lo;
@@ -52,6 +57,8 @@ attention_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     int len = S;
     if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[b], 0));
     if (MASK == MASK_CAUSAL) len = min(len, qrow + 1);
+    float* sc = s_sc[wib];
+    // ---- phase 1: scores (log2 domain)
     float q[HD];
     {
         const uint4* qp = reinterpret_cast<const uint4*>(seq + (size_t)qrow * ld + h * HD);
@@ -67,60 +74,53 @@ attention_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
             }
         }
     }
-    float m = -INFINITY, l = 0.f;
-    float o[HD];
-#pragma unroll
-    for (int i = 0; i < HD; ++i) o[i] = 0.f;
+    float m = -INFINITY;
+#pragma unroll 2
     for (int key = lane; key < len; key += 32) {
         const uint4* kp = reinterpret_cast<const uint4*>(seq + (size_t)key * ld + W + h * HD);
-        const uint4* vp = reinterpret_cast<const uint4*>(seq + (size_t)key * ld + 2 * W + h * HD);
-        float sc = 0.f;
+        uint4 k4[HD / 8];
+#pragma unroll
+        for (int u = 0; u < HD / 8; ++u) k4[u] = __ldg(kp + u);
+        float acc = 0.f;
 #pragma unroll
         for (int u = 0; u < HD / 8; ++u) {
-            const uint4 k4 = __ldg(kp + u);
-            const uint32_t w4[4] = {k4.x, k4.y, k4.z, k4.w};
+            const uint32_t w4[4] = {k4[u].x, k4[u].y, k4[u].z, k4[u].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
-                sc = fmaf(q[8 * u + 2 * e], f2.x, sc);
-                sc = fmaf(q[8 * u + 2 * e + 1], f2.y, sc);
+                acc = fmaf(q[8 * u + 2 * e], f2.x, acc);
+                acc = fmaf(q[8 * u + 2 * e + 1], f2.y, acc);
             }
         }
-        const float m_new = fmaxf(m, sc);
-        const float alpha = ex2(m - m_new);
-        const float pe = ex2(sc - m_new);
-        const float pb = __bfloat162float(__float2bfloat16_rn(pe));  // same P rounding as the tensor-core path
-        l = l * alpha + pe;
-        m = m_new;
-#pragma unroll
-        for (int u = 0; u < HD / 8; ++u) {
-            const uint4 v4 = __ldg(vp + u);
-            const uint32_t w4[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
-                o[8 * u + 2 * e] = fmaf(o[8 * u + 2 * e], alpha, pb * f2.x);
-                o[8 * u + 2 * e + 1] = fmaf(o[8 * u + 2 * e + 1], alpha, pb * f2.y);
-            }
-        }
+        sc[key] = acc;
+        m = fmaxf(m, acc);
     }
-    // merge the 32 partial softmaxes
-    float mg = m;
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) mg = fmaxf(mg, __shfl_xor_sync(0xffffffffu, mg, off));
-    const float corr = m == -INFINITY ? 0.f : ex2(m - mg);
-    l *= corr;
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    __syncwarp();
+    // ---- softmax numerators (fp32 sum; bf16-rounded P for the PV product, like the tensor-core path)
+    float l = 0.f;
+    for (int key = lane; key < len; key += 32) {
+        const float pe = ex2(sc[key] - m);
+        l += pe;
+        sc[key] = __bfloat162float(__float2bfloat16_rn(pe));
+    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat16* dst = out + ((size_t)b * S + qrow) * W + h * HD;
-#pragma unroll
-    for (int i = 0; i < HD; ++i) {
-        float v = o[i] * corr;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-        if (lane == (i & 31)) dst[i] = __float2bfloat16_rn(v * inv);
+    __syncwarp();
+    // ---- phase 2: out[d] = sum_j p_j V[j][d]; lane owns dims 2*lane, 2*lane+1
+    const __nv_bfloat162* vcol = reinterpret_cast<const __nv_bfloat162*>(seq + 2 * W + h * HD) + lane;
+    float ox = 0.f, oy = 0.f;
+#pragma unroll 8
+    for (int key = 0; key < len; ++key) {
+        const float2 v2 = __bfloat1622float2(vcol[(size_t)key * (ld / 2)]);
+        const float pj = sc[key];
+        ox = fmaf(pj, v2.x, ox);
+        oy = fmaf(pj, v2.y, oy);
     }
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * S + qrow) * W + h * HD) + lane;
+    *dst = __floats2bfloat162_rn(ox * inv, oy * inv);
 }
 
 template <int MASK>
@@ -441,7 +441,7 @@ void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W
     // A short remainder (S = 257, 129, ...) is not worth a 128-wide tile in either dimension.
     constexpr int TAIL_MAX = 8;
     const int rem = S % tc::BQ;
-    const bool tail = S >= tc::BQ && rem > 0 && rem <= TAIL_MAX;
+    const bool tail = S >= tc::BQ && rem > 0 && rem <= TAIL_MAX && S <= tc::TAIL_S_MAX;
     const int s_main = tail ? S - rem : S;                       // keys handled by the tensor cores
     const int q_blocks = tail ? S / tc::BQ : (S + tc::BQ - 1) / tc::BQ;
     const dim3 grid(q_blocks, H, B);

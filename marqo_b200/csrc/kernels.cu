@@ -257,8 +257,8 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
     return t;
 }
 
-// CLIP head: 8 images per CTA so that every element of the fp32 projection matrix read from L2 feeds 8 FMAs.
-constexpr int HEAD_IMGS = 8;
+// CLIP head: 4 images per CTA so that every element of the fp32 projection matrix read from L2 feeds 4 FMAs.
+constexpr int HEAD_IMGS = 4;
 
 __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict__ x, int S, const int32_t* __restrict__ row_in_seq,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict_
     float* res = sh + (size_t)w * HEAD_IMGS;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b0 = blockIdx.x * HEAD_IMGS;
-    {   // LayerNorm: warp k normalises image b0 + k (two-pass, like layernorm_kernel)
+    if (warp < HEAD_IMGS) {   // LayerNorm: warp k normalises image b0 + k (two-pass, like layernorm_kernel)
         const int b = b0 + warp;
         if (b < n) {
             const int r = row_in_seq ? row_in_seq[b] : 0;
@@ -297,18 +297,14 @@ __global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict_
         float acc[HEAD_IMGS];
 #pragma unroll
         for (int k = 0; k < HEAD_IMGS; ++k) acc[k] = 0.f;
+#pragma unroll 8
         for (int i = 0; i < w; ++i) {
             const float pj = __ldg(proj + (long long)i * E + e);
             const float4 a = *reinterpret_cast<const float4*>(pooledT + i * HEAD_IMGS);
-            const float4 c = *reinterpret_cast<const float4*>(pooledT + i * HEAD_IMGS + 4);
             acc[0] = fmaf(a.x, pj, acc[0]);
             acc[1] = fmaf(a.y, pj, acc[1]);
             acc[2] = fmaf(a.z, pj, acc[2]);
             acc[3] = fmaf(a.w, pj, acc[3]);
-            acc[4] = fmaf(c.x, pj, acc[4]);
-            acc[5] = fmaf(c.y, pj, acc[5]);
-            acc[6] = fmaf(c.z, pj, acc[6]);
-            acc[7] = fmaf(c.w, pj, acc[7]);
         }
 #pragma unroll
         for (int k = 0; k < HEAD_IMGS; ++k) {

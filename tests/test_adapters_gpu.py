@@ -192,3 +192,26 @@ def test_gpu_tensor_index_feed_query_highlights_overwrite_delete(gpu_required):
                          _doc("ok", {}, {"title": (["t"], unit(1))})], "s1")
     assert bad.errors and bad.responses[0].status == 400 and bad.responses[1].status == 200
     ix.close()
+
+
+def test_concurrent_encode_calls_are_serialised_per_handle(gpu_required):
+    """Marqo calls encode() from up to 16 request threads with no lock; the handle serialises internally."""
+    import threading
+    from marqo_b200 import weights as Wt
+    from marqo_b200.engine import Encoder
+    enc = Encoder("bert", TINY_BERT_ARCH, Wt.random_bert_weights(TINY_BERT_ARCH, 3), max_batch=16)
+    rng = np.random.default_rng(0)
+    inputs = [rng.integers(1, 999, size=(int(rng.integers(1, 12)), int(rng.integers(2, 60)))).astype(np.int32) for _ in range(24)]
+    serial = [enc.encode_tokens(x) for x in inputs]
+    out = [None] * len(inputs)
+
+    def work(lo):
+        for i in range(lo, len(inputs), 6):
+            out[i] = enc.encode_tokens(inputs[i])
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for a, b in zip(serial, out):
+        np.testing.assert_array_equal(a, b)          # same kernels, same order of arithmetic -> bitwise equal
+    enc.close()

@@ -257,3 +257,50 @@ def test_sharded_search_allgather_merge_gloo_world2(native_lib, score_oracle, tm
         out, _ = p.communicate(timeout=240)
         assert p.returncode == 0, out
         assert "ok" in out
+
+
+# ------------------------------------------------------------------------------------------------ model-cache concurrency
+def test_concurrent_model_load_is_rejected_like_the_reference(monkeypatch):
+    """tests/s2_inference/test_automatic_model_ejection_and_concurrency.py:135-254 of the reference: a request that
+    needs to load a model while another load holds the lock fails fast with ModelCacheManagementError."""
+    import threading
+    import time
+    from marqo_b200 import loaders, s2_inference as s2
+    from marqo_b200.errors import ModelCacheManagementError
+
+    started, release = threading.Event(), threading.Event()
+
+    class SlowModel:
+        def __init__(self, device=None, model_properties=None, model_auth=None):
+            pass
+
+        def load(self):
+            started.set()
+            release.wait(timeout=20)
+
+        def encode(self, content, normalize=True, **kw):
+            items = [content] if isinstance(content, str) else list(content)
+            return np.ones((len(items), 4), np.float32)
+
+    monkeypatch.setattr(loaders, "get_model_loader", lambda name, props: SlowModel)
+    s2.clear_loaded_models()
+    props_a = {"name": "slow-a", "dimensions": 4, "type": "hf", "arch": {}}
+    props_b = {"name": "slow-b", "dimensions": 4, "type": "hf", "arch": {}}
+    result = {}
+
+    def first():
+        result["a"] = s2.vectorise("slow-a", ["x"], model_properties=props_a, device="cuda:0")
+
+    t = threading.Thread(target=first)
+    t.start()
+    assert started.wait(timeout=10)
+    try:
+        with pytest.raises(ModelCacheManagementError):
+            s2.vectorise("slow-b", ["y"], model_properties=props_b, device="cuda:0")
+    finally:
+        release.set()
+        t.join(timeout=20)
+    assert result["a"] == [[1.0, 1.0, 1.0, 1.0]]
+    # once loaded, concurrent encode() calls need no lock (the reference only locks loading, s2_inference.py:293-298)
+    assert s2.vectorise("slow-a", ["x", "y"], model_properties=props_a, device="cuda:0") == [[1.0] * 4, [1.0] * 4]
+    s2.clear_loaded_models()
