@@ -20,8 +20,11 @@ template <int BN>
 struct Cfg {
     static constexpr uint32_t B_STAGE_BYTES = (BN / 2) * BK * 2;   // each CTA of the pair holds half of the W tile
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    static constexpr int STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES > 8 ? 8 : (SMEM_LIMIT - 2048) / STAGE_BYTES;
-    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    // per epilogue warp: a 32-row x 128-byte transpose buffer (coalesced global I/O) + a 128-byte bias row
+    static constexpr uint32_t EPI_BYTES = 8 /*EPI_WARPS*/ * (32 * 128 + 128);
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - (int)EPI_BYTES) / (int)STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;
     static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN < 32 ? 32 : ACC_STAGES * BN;
 };
 
@@ -83,7 +86,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + (size_t)C::STAGES * A_STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint8_t* smem_epi = smem + (size_t)C::STAGES * C::STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;
     uint64_t* tempty = tfull + ACC_STAGES;
@@ -179,33 +183,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
         }
     } else if (warp >= 2) {
-        // ---------------------------------------------------------------- epilogue (TMEM -> regs -> global)
+        // ---------------------------------------------------------------- epilogue (TMEM -> regs -> smem -> global)
         // A warp may only read the TMEM lanes of sub-partition (warp % 4); the two warps that share a sub-partition
-        // split the tile's columns in halves, so 8 warps drain one 128 x BN accumulator.
+        // split the tile's columns in halves, so 8 warps drain one 128 x BN accumulator.  TMEM hands every lane one ROW
+        // (32 consecutive columns); global memory wants whole 128-byte lines per instruction, so each warp transposes
+        // through a private, XOR-swizzled 32 x 128 B shared-memory buffer in both directions (residual in, result out).
         const int sp = warp & 3;
         const int half = (warp - 2) >> 2;
         constexpr int HALF_COLS = BN / 2 >= 32 ? BN / 2 : 32;
         constexpr int CHUNKS = HALF_COLS / 32;
         const bool has_cols = half * HALF_COLS < BN;  // BN = 32 would leave the second half empty
         const Epilogue& ep = p.ep;
+        uint8_t* stage_buf = smem_epi + (size_t)(warp - 2) * (32 * 128 + 128);
+        float* bias_row = reinterpret_cast<float*>(stage_buf + 32 * 128);
+        const int esz = ep.out_fp32 ? 4 : 2;                  // output element size
+        const int cols_per_flush = 128 / esz;                 // 32 fp32 or 64 bf16 columns fill a 128-byte row
+        // bf16 results are staged two chunks (64 columns) per flush; a residual block occupies the whole buffer, so
+        // residual GEMMs (fp32 out in this engine) flush after every chunk
+        const int chunks_per_flush = (ep.out_fp32 || ep.residual) ? 1 : cols_per_flush / 32;
+        const int srow = lane >> 3, sunit = lane & 7;         // coalesced phase: 4 rows x 8 sixteen-byte units per instr
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < num_super; t += num_clusters) {
             const int m0 = ((t / p.tiles_n) * CLUSTER + (int)crank) * BM;
             const int nt0 = (t % p.tiles_n) * BN + half * HALF_COLS;
-            const int row = m0 + sp * 32 + lane;
-            const bool row_ok = row < p.M;
-            long long orow = row;
-            int brow = 0;
-            if (ep.remap_group > 0) {
-                const int b = row / ep.remap_group, i = row - b * ep.remap_group;
-                orow = (long long)b * (ep.remap_group + 1) + 1 + i;
-                brow = 1 + i;
-            }
+            const int wrow0 = m0 + sp * 32;                   // first row of this warp's 32-row band
             if (ep.residual && has_cols) {
-                // pull the residual segment this thread will need for its NEXT tile towards L2 (one tile ahead: the
-                // loads below then hit L2 instead of paying HBM latency inside the serial chunk loop); the very first
-                // tile prefetches for itself.
+                // pull the residual band this warp needs for its NEXT tile towards L2 (the very first tile: itself)
                 for (int pass = (t == cluster_id ? 0 : 1); pass < 2; ++pass) {
                     const int tn = t + pass * num_clusters;
                     if (tn >= num_super) break;
@@ -223,6 +227,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             ptx::tc_fence_after();
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c) {
+                const int n0 = nt0 + c * 32;
+                const bool cols_ok = has_cols && n0 < p.N;
+                // (1) start the long-latency global reads first: bias (one float per lane) and, for residual GEMMs,
+                //     the 32 x 32 fp32 residual block in coalesced order (4 rows x 128 B per instruction)
+                float bias_v = 0.f;
+                if (ep.bias && cols_ok) bias_v = __ldg(ep.bias + n0 + lane);
+                float4 rres[8];
+                if (ep.residual && cols_ok) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = wrow0 + i * 4 + srow;
+                        rres[i] = rr < p.M ? *reinterpret_cast<const float4*>(ep.residual + (size_t)rr * ep.ldr + n0 + sunit * 4)
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                // (2) accumulator chunk: lane == row
                 uint32_t v[32];
                 if (has_cols) {
                     ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(sp * 32) << 16) + acc * BN + half * HALF_COLS + c * 32, v);
@@ -234,27 +254,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty[acc]), 0));
                 }
-                const int n0 = nt0 + c * 32;
-                if (has_cols && row_ok && n0 < p.N) {
+                if (cols_ok) {
+                    bias_row[lane] = bias_v;
+                    if (ep.residual) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = i * 4 + srow;
+                            *reinterpret_cast<float4*>(stage_buf + rr * 128 + ((sunit ^ (rr & 7)) << 4)) = rres[i];
+                        }
+                    }
+                    __syncwarp();
                     float f[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                    if (ep.bias) {
-                        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 b = __ldg(b4 + j);
-                            f[4 * j] += b.x;
-                            f[4 * j + 1] += b.y;
-                            f[4 * j + 2] += b.z;
-                            f[4 * j + 3] += b.w;
-                        }
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias_row + 4 * j);   // broadcast read
+                        f[4 * j] = __uint_as_float(v[4 * j]) + b.x;
+                        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
                     }
                     if (ep.act != ACT_NONE) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
                     }
-                    if (ep.rowbias) {
+                    if (ep.rowbias) {   // ViT patch-embed: positional embedding of this lane's patch
+                        const int row = wrow0 + lane;
+                        const int brow = 1 + row % ep.remap_group;
                         const float4* r4 = reinterpret_cast<const float4*>(ep.rowbias + (size_t)brow * p.N + n0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -266,30 +291,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         }
                     }
                     if (ep.residual) {
-                        const float4* r4 = reinterpret_cast<const float4*>(ep.residual + (size_t)row * ep.ldr + n0);
-                        float4 rr[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) rr[j] = r4[j];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            f[4 * j] += rr[j].x;
-                            f[4 * j + 1] += rr[j].y;
-                            f[4 * j + 2] += rr[j].z;
-                            f[4 * j + 3] += rr[j].w;
+                            const float4 b = *reinterpret_cast<const float4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                            f[4 * j] += b.x;
+                            f[4 * j + 1] += b.y;
+                            f[4 * j + 2] += b.z;
+                            f[4 * j + 3] += b.w;
                         }
+                        __syncwarp();   // everyone has read its residual row before the buffer is overwritten
                     }
+                    // (3) own row -> staging buffer (swizzled 16-byte units)
                     if (ep.out_fp32) {
-                        float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo + n0);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     } else {
-                        uint4* o4 =
-                            reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)orow * ep.ldo + n0);
+                        const int ubase = (c % chunks_per_flush) * 4;   // this chunk fills units 0-3 or 4-7 of the row
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(stage_buf + lane * 128 + (((ubase + j) ^ (lane & 7)) << 4)) =
+                                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
                     }
+                }
+                // (4) flush full 128-byte rows: every instruction writes 4 rows x 128 contiguous bytes
+                const bool flush = (c % chunks_per_flush) == chunks_per_flush - 1 || c == CHUNKS - 1;
+                if (flush && has_cols) {
+                    __syncwarp();
+                    const int fc0 = nt0 + (c / chunks_per_flush) * chunks_per_flush * 32;   // first column held in the buffer
+                    const int col = fc0 + sunit * (16 / esz);
+                    const int filled_units = ((c % chunks_per_flush) + 1) * (32 * esz / 16);
+                    if (col < p.N && sunit < filled_units) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = i * 4 + srow;
+                            const int grow = wrow0 + rr;
+                            if (grow < p.M) {
+                                long long orow = grow;
+                                if (ep.remap_group > 0) {
+                                    const int b = grow / ep.remap_group;
+                                    orow = (long long)b * (ep.remap_group + 1) + 1 + (grow - b * ep.remap_group);
+                                }
+                                const uint4 val = *reinterpret_cast<const uint4*>(stage_buf + rr * 128 + ((sunit ^ (rr & 7)) << 4));
+                                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ep.out) +
+                                                          ((size_t)orow * ep.ldo + col) * esz) = val;
+                            }
+                        }
+                    }
+                    __syncwarp();
                 }
             }
             if (++acc == ACC_STAGES) {
