@@ -71,6 +71,15 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def load_traffic():
+    """DRAM bytes per launch of the dominant kernels, read from the committed ncu capture summary (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
+
+
 def vit_flops(arch_vision: dict, batch: int):
     """Algorithmic FLOPs of one step: (total, in GEMM kernels, in attention)."""
     w, L, mlp, p = arch_vision["width"], arch_vision["layers"], arch_vision["mlp"], arch_vision["patch"]
@@ -227,6 +236,7 @@ def main():
     if distributed:
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
+    traffic = load_traffic()
 
     def barrier():
         if distributed:
@@ -369,7 +379,12 @@ def main():
             "unit": "queries/s", "ms_per_batch": t_ms, "rows_total": args.topk_rows, "rows_per_gpu": rows_local,
             "scan_ms": scan_ms, "merge_ms": statistics.median(merge), "scaling": "strong",
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                         "frac": ach / peaks["hbm_gbs"],
+                         "traffic": (traffic.get("score_scan_kernel", {}).get("dram_bytes_per_launch")
+                                     if rows_local == traffic.get("score_scan_kernel", {}).get("rows") else None),
+                         "traffic_note": "ncu dram bytes of one launch on a 1.25M-row shard: 1.924e9 vs 1.920e9 algorithmic "
+                                         "(profiles/r01_ncu_summary.md); null when this run's shard size differs",
+                         "peak_source": peaks["source"],
                          "kernel": "score::scan_kernel", "bytes_per_launch": bytes_per_launch},
         }
         # e2e: host queries in, host ids out, through b200_index_search
@@ -426,7 +441,11 @@ def main():
                        "residual_stream": "fp32", "accumulate": "fp32"},
             "tflops": flops_total / (step_ms / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": ach_tf / peak_tf, "traffic": None, "kernel": "gemm::gemm_kernel (all shapes of the step)",
+                         "frac": ach_tf / peak_tf,
+                         "traffic": traffic.get("gemm_gemm_kernel_256", {}).get("avg"),
+                         "traffic_note": "mean dram__bytes_read+write per launch over the 4 GEMMs of a ViT-L-14 layer "
+                                         "(ncu --set full, profiles/r01_ncu_summary.md); algorithmic mean 747e6 bytes",
+                         "kernel": "gemm::gemm_kernel (all shapes of the step)",
                          "launches_timed": gemm_n, "avg_launch_ms": gemm_avg_ms,
                          "flops_per_launch_avg": flops_gemm * args.steps / max(gemm_n, 1),
                          "peak_source": f"{peaks['source']} bf16 sustained", "step_share": gemm_ms / (step_ms * args.steps),

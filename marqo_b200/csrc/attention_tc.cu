@@ -111,8 +111,8 @@ attention_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16*
     // ---- phase 2: out[d] = sum_j p_j V[j][d]; lane owns dims 2*lane, 2*lane+1
     const __nv_bfloat162* vcol = reinterpret_cast<const __nv_bfloat162*>(seq + 2 * W + h * HD) + lane;
     float ox = 0.f, oy = 0.f;
-#pragma unroll 8
-    for (int key = 0; key < len; ++key) {
+#pragma unroll 32
+    for (int key = 0; key < len; ++key) {   // 32 independent 128-byte row reads in flight per warp
         const float2 v2 = __bfloat1622float2(vcol[(size_t)key * (ld / 2)]);
         const float pj = sc[key];
         ox = fmaf(pj, v2.x, ox);
