@@ -50,6 +50,7 @@ struct ScanParams {
     int num_stages;
     int nq;
     const int32_t* doc_of_row;  // used when HAS_DOCS
+    const float* row_bias;      // used when HAS_BIAS: score = 2 * dot - row_bias[row]  (euclidean: |row|^2)
     const float* bound_score;   // optional [MQ]: only rows strictly after (bound_score, bound_row) qualify
     const int32_t* bound_row;
     float* out_score;           // [grid][MQ][KP]
@@ -58,7 +59,7 @@ struct ScanParams {
 };
 
 __host__ __device__ inline size_t scan_smem_bytes(int dim, int stages) {
-    return (size_t)(dim / BLOCK_K) * QCHUNK_BYTES + (size_t)stages * STAGE_BYTES + 4 * TILE_N * sizeof(int32_t) +
+    return (size_t)(dim / BLOCK_K) * QCHUNK_BYTES + (size_t)stages * STAGE_BYTES + 2 * 4 * TILE_N * sizeof(int32_t) +
            (2 * 16 + 2 * ACC_STAGES + 2) * sizeof(uint64_t) + 1024 /* alignment slack */;
 }
 
@@ -111,7 +112,7 @@ __device__ __forceinline__ void list_insert(float (&ls)[KP], int (&lr)[KP], int 
     }
 }
 
-template <bool HAS_DOCS>
+template <bool HAS_DOCS, bool HAS_BIAS>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_q, ScanParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -121,7 +122,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ 
     uint8_t* smem_q = smem;
     uint8_t* smem_c = smem_q + (size_t)kblocks * QCHUNK_BYTES;
     int32_t* smem_docs = reinterpret_cast<int32_t*>(smem_c + (size_t)S * STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_docs + 4 * TILE_N);
+    float* smem_bias = reinterpret_cast<float*>(smem_docs + 4 * TILE_N);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_bias + 4 * TILE_N);
     uint64_t* empty = full + 16;
     uint64_t* tfull = empty + 16;
     uint64_t* tempty = tfull + ACC_STAGES;
@@ -216,6 +218,7 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ 
         const int q = sp * 16 + lane;  // M = 64 accumulator: row m lives in lane (m % 16) of sub-partition m / 16
         const bool active = lane < 16 && q < p.nq;
         int32_t* my_docs = smem_docs + (warp - 2) * TILE_N;
+        float* my_bias = smem_bias + (warp - 2) * TILE_N;
         float ls[KP];
         int lr[KP], ld[KP];
 #pragma unroll
@@ -236,12 +239,13 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ 
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int row0 = tile * TILE_N;
-            if (HAS_DOCS) {
+            if (HAS_DOCS || HAS_BIAS) {
                 __syncwarp();
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     int r = row0 + t * 32 + lane;
-                    my_docs[t * 32 + lane] = r < p.n_rows ? __ldg(p.doc_of_row + r) : -1;
+                    if (HAS_DOCS) my_docs[t * 32 + lane] = r < p.n_rows ? __ldg(p.doc_of_row + r) : -1;
+                    if (HAS_BIAS) my_bias[t * 32 + lane] = r < p.n_rows ? __ldg(p.row_bias + r) : 0.f;
                 }
                 __syncwarp();
             }
@@ -254,6 +258,11 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ 
                 ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(sp * 32) << 16) + acc * TILE_N + c * 32, v);
                 ptx::tmem_ld_wait();
                 if (active) {
+                    if (HAS_BIAS) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            v[j] = __float_as_uint(fmaf(2.0f, __uint_as_float(v[j]), -my_bias[c * 32 + j]));
+                    }
                     uint32_t mask = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(v[j]) > thr) ? (1u << j) : 0u;
@@ -328,8 +337,11 @@ __device__ __forceinline__ bool approx_before(float sa, int ra, float sb, int rb
     return sa > sb || (sa == sb && ra < rb);
 }
 
+// `val` is the exact ordering key of the re-score pass: the dot product, or minus the squared distance (euclidean)
 __device__ __forceinline__ double closeness_from_dot(double dot, int metric) {
     switch (metric) {
+        case B200_METRIC_EUCLIDEAN:
+            return 1.0 / (1.0 + sqrt(fmax(-dot, 0.0)));
         case B200_METRIC_PRENORMALIZED_ANGULAR:
             return 1.0 / (1.0 + (1.0 - dot));
         case B200_METRIC_ANGULAR: {
@@ -462,7 +474,14 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeParams p) {
         const __half* qv = p.qh + (size_t)q * p.dim;
         const __half* cv = p.corpus + (size_t)sel_row[c] * p.dim;
         double part = 0.0;
-        for (int i = lane; i < p.dim; i += 32) part += (double)__half2float(qv[i]) * (double)__half2float(cv[i]);
+        if (p.metric == B200_METRIC_EUCLIDEAN) {
+            for (int i = lane; i < p.dim; i += 32) {
+                const double d = (double)__half2float(qv[i]) - (double)__half2float(cv[i]);   // exact in fp64
+                part -= d * d;
+            }
+        } else {
+            for (int i = lane; i < p.dim; i += 32) part += (double)__half2float(qv[i]) * (double)__half2float(cv[i]);
+        }
         double tot = 0.0;
         for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);
         if (lane == 0) sel_dot[c] = tot;
@@ -503,7 +522,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeParams p) {
 // ------------------------------------------------------------------------------------------------
 // fp32 -> fp16 row conversion (optionally L2-normalising first, for the angular metric).
 __global__ void convert_rows_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t rows, int dim,
-                                    int64_t dst_rows_total, int normalize) {
+                                    int64_t dst_rows_total, int normalize, float* __restrict__ n2_out = nullptr) {
     // one warp per row; rows in [rows, dst_rows_total) are zero-filled (query padding)
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -521,7 +540,30 @@ __global__ void convert_rows_kernel(const float* __restrict__ src, __half* __res
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         scale = ss > 0.f ? 1.0f / sqrtf(ss) : 0.f;
     }
-    for (int i = lane; i < dim; i += 32) d[i] = __float2half_rn(s[i] * scale);
+    float n2 = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const __half hv = __float2half_rn(s[i] * scale);
+        d[i] = hv;
+        const float f = __half2float(hv);
+        n2 = fmaf(f, f, n2);
+    }
+    if (n2_out) {   // |row|^2 of the STORED (fp16-rounded) values: the euclidean scan's per-row term
+        for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+        if (lane == 0) n2_out[row] = n2;
+    }
+}
+
+__global__ void row_norms_kernel(const __half* __restrict__ rows, int64_t n, int dim, float* __restrict__ n2_out) {
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float n2 = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float f = __half2float(rows[row * dim + i]);
+        n2 = fmaf(f, f, n2);
+    }
+    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    if (lane == 0) n2_out[row] = n2;
 }
 
 __global__ void iota_kernel(int32_t* dst, int64_t n, int32_t start) {
@@ -570,6 +612,7 @@ struct b200_index {
     bool has_docs = false;  // false while doc_of_row[i] == i for every row (identity fast path)
     __half* corpus = nullptr;
     int32_t* doc_of_row = nullptr;
+    float* row_n2 = nullptr;       // [capacity] squared norms (euclidean metric only)
     // per-search workspaces
     __half* qh = nullptr;          // [MQ, dim]
     float* q_stage = nullptr;      // [MQ, dim] fp32 staging for host queries
@@ -595,6 +638,7 @@ void index_free(b200_index* ix) {
     cudaSetDevice(ix->device);
     cudaFree(ix->corpus);
     cudaFree(ix->doc_of_row);
+    cudaFree(ix->row_n2);
     cudaFree(ix->qh);
     cudaFree(ix->q_stage);
     cudaFree(ix->list_score);
@@ -636,11 +680,19 @@ void ensure_capacity(b200_index* ix, int64_t need_rows) {
         MB_CUDA(cudaMemcpyAsync(nd, ix->doc_of_row, (size_t)ix->n_rows * sizeof(int32_t), cudaMemcpyDeviceToDevice,
                                 ix->stream));
     }
+    float* nn = nullptr;
+    if (ix->metric == B200_METRIC_EUCLIDEAN) {
+        cuda_alloc((void**)&nn, (size_t)cap * sizeof(float));
+        if (ix->n_rows > 0)
+            MB_CUDA(cudaMemcpyAsync(nn, ix->row_n2, (size_t)ix->n_rows * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+    }
     MB_CUDA(cudaStreamSynchronize(ix->stream));
     cudaFree(ix->corpus);
     cudaFree(ix->doc_of_row);
+    cudaFree(ix->row_n2);
     ix->corpus = nc;
     ix->doc_of_row = nd;
+    ix->row_n2 = nn;
     ix->capacity = cap;
 }
 
@@ -657,7 +709,6 @@ b200_index* index_new(int device, int dim, int metric, int64_t capacity_rows) {
     MB_CHECK_ARG(dim > 0 && dim % BLOCK_K == 0 && dim <= MAX_DIM, "dim must be a multiple of %d and <= %d (got %d)",
                  BLOCK_K, MAX_DIM, dim);
     MB_CHECK_ARG(metric >= 0 && metric <= B200_METRIC_EUCLIDEAN, "unknown metric %d", metric);
-    if (metric == B200_METRIC_EUCLIDEAN) fail(B200_ERR_UNSUPPORTED, "euclidean metric is not implemented yet");
     MB_CHECK_ARG(capacity_rows >= 0, "capacity_rows must be >= 0");
     DeviceGuard g(device);
     b200_index* ix = new b200_index();
@@ -683,8 +734,10 @@ b200_index* index_new(int device, int dim, int metric, int64_t capacity_rows) {
         cuda_alloc((void**)&ix->bound_score, (size_t)MQ * sizeof(float));
         cuda_alloc((void**)&ix->bound_row, (size_t)MQ * sizeof(int32_t));
         ensure_capacity(ix, std::max<int64_t>(capacity_rows, TILE_N));
-        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
         MB_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     } catch (...) {
         index_free(ix);
@@ -698,7 +751,8 @@ void add_rows_device(b200_index* ix, const float* d_vecs, const int32_t* d_doc_i
     const int wpb = 8;
     const int64_t blocks = (m + wpb - 1) / wpb;
     convert_rows_kernel<<<(unsigned)blocks, wpb * 32, 0, ix->stream>>>(
-        d_vecs, ix->corpus + (size_t)ix->n_rows * ix->dim, m, ix->dim, m, ix->metric == B200_METRIC_ANGULAR);
+        d_vecs, ix->corpus + (size_t)ix->n_rows * ix->dim, m, ix->dim, m, ix->metric == B200_METRIC_ANGULAR,
+        ix->metric == B200_METRIC_EUCLIDEAN ? ix->row_n2 + ix->n_rows : nullptr);
     MB_CUDA(cudaGetLastError());
     if (d_doc_ids) {
         MB_CUDA(cudaMemcpyAsync(ix->doc_of_row + ix->n_rows, d_doc_ids, (size_t)m * sizeof(int32_t),
@@ -741,6 +795,7 @@ void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_
     sp.num_stages = stages;
     sp.nq = nq;
     sp.doc_of_row = ix->doc_of_row;
+    sp.row_bias = ix->row_n2;
     sp.bound_score = bound_score;
     sp.bound_row = bound_row;
     sp.out_score = ix->list_score;
@@ -748,10 +803,15 @@ void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_
     sp.out_doc = ix->list_doc;
 
     if (record_timing) MB_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
-    if (ix->has_docs)
-        scan_kernel<true><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
+    const bool bias = ix->metric == B200_METRIC_EUCLIDEAN;
+    if (ix->has_docs && bias)
+        scan_kernel<true, true><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
+    else if (ix->has_docs)
+        scan_kernel<true, false><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
+    else if (bias)
+        scan_kernel<false, true><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
     else
-        scan_kernel<false><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
+        scan_kernel<false, false><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
     MB_CUDA(cudaGetLastError());
     if (record_timing) MB_CUDA(cudaEventRecord(ix->ev[1], ix->stream));
 
@@ -1159,6 +1219,12 @@ int b200_index_load(int device, const char* path, b200_index** out) {
             slurp(ix->doc_of_row, (size_t)hdr.n_rows * sizeof(int32_t));
             ix->n_rows = hdr.n_rows;
             ix->has_docs = hdr.has_docs != 0;
+            if (ix->metric == B200_METRIC_EUCLIDEAN && hdr.n_rows > 0) {
+                row_norms_kernel<<<(unsigned)((hdr.n_rows + 7) / 8), 256, 0, ix->stream>>>(ix->corpus, hdr.n_rows, hdr.dim,
+                                                                                         ix->row_n2);
+                MB_CUDA(cudaGetLastError());
+                MB_CUDA(cudaStreamSynchronize(ix->stream));
+            }
         } catch (...) {
             fclose(f);
             index_free(ix);

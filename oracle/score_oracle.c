@@ -13,7 +13,7 @@
  *     src/marqo/core/unstructured_vespa_index/unstructured_vespa_schema.py:155-166,225-230,292-294
  *   - closeness = 1 / (1 + distance); distance by `distance-metric`
  *     (src/marqo/core/models/marqo_index.py:63-69): prenormalized-angular 1 - q.e,
- *     angular acos(cos), dotproduct: closeness = q.e (raw)
+ *     angular acos(cos), dotproduct: closeness = q.e (raw), euclidean |q - e|
  *   - pinned by the reference's tests: identical vector => _score == 1.0
  *     (tests/tensor_search/integ_tests/test_custom_vector_field.py:592,602)
  *
@@ -120,8 +120,26 @@ static double exact_dot_f(const float* q, const float* c, int dim) {
     return tot;
 }
 
+/* euclidean: the ordering key is minus the squared distance, sum of exact (q - c)^2 terms in the same fixed order */
+static double exact_neg_sqdist_f(const float* q, const float* c, int dim) {
+    double part[32];
+    for (int l = 0; l < 32; ++l) part[l] = 0.0;
+    for (int i = 0; i < dim; i += 32)
+        for (int l = 0; l < 32 && i + l < dim; ++l) {
+            double d = (double)q[i + l] - (double)c[i + l];
+            part[l] -= d * d;
+        }
+    double tot = 0.0;
+    for (int l = 0; l < 32; ++l) tot += part[l];
+    return tot;
+}
+
 double oracle_closeness(double dot, int metric) {
     switch (metric) {
+        case 3: { /* euclidean: `dot` carries -|q - e|^2 */
+            double d2 = -dot;
+            return 1.0 / (1.0 + sqrt(d2 > 0.0 ? d2 : 0.0));
+        }
         case 0: /* prenormalized-angular */
             return 1.0 / (1.0 + (1.0 - dot));
         case 1: { /* angular */
@@ -176,7 +194,8 @@ int oracle_search(const uint16_t* qh, int nq, const uint16_t* corpus, int64_t n,
             for (int64_t r = 0; r < nb; ++r) {
                 int32_t d = doc_of_row ? doc_of_row[r0 + r] : (int32_t)(r0 + r);
                 if (d < 0) continue; /* deleted row */
-                double dot = exact_dot_f(qf + (size_t)q * dim, cf + (size_t)r * dim, dim);
+                double dot = metric == 3 ? exact_neg_sqdist_f(qf + (size_t)q * dim, cf + (size_t)r * dim, dim)
+                                         : exact_dot_f(qf + (size_t)q * dim, cf + (size_t)r * dim, dim);
                 if (rq[d] < 0 || dot > bq[d]) { /* ties keep the lowest row */
                     bq[d] = dot;
                     rq[d] = (int32_t)(r0 + r);

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _LIB = None
 
-METRICS = {"prenormalized-angular": 0, "angular": 1, "dotproduct": 2}
+METRICS = {"prenormalized-angular": 0, "angular": 1, "dotproduct": 2, "euclidean": 3}
 
 
 def _lib() -> C.CDLL:

@@ -57,15 +57,24 @@ def test_self_match_and_duplicates(gpu_required, score_oracle):
     _check(store, score_oracle, q, corpus, 10, "prenormalized-angular")
 
 
-@pytest.mark.parametrize("metric", ["angular", "dotproduct"])
+@pytest.mark.parametrize("metric", ["angular", "dotproduct", "euclidean"])
 def test_other_metrics(gpu_required, score_oracle, metric):
     from marqo_b200.engine import RowStore
     rng = np.random.default_rng(9)
     corpus = rng.standard_normal((3000, 256)).astype(np.float32)
     q = rng.standard_normal((9, 256)).astype(np.float32)
     store = RowStore(256, metric=metric)
-    store.add(corpus)
+    store.add(corpus[:1000])
+    store.add(corpus[1000:])
     _check(store, score_oracle, q, corpus, 10, metric)
+    doc_of_row = (np.arange(3000) // 2).astype(np.int32)
+    chunks = RowStore(256, metric=metric)
+    chunks.add(corpus, doc_of_row)
+    _check(chunks, score_oracle, q, corpus, 25, metric, doc_of_row)
+    if metric == "euclidean":
+        d, r, s = store.search(corpus[5:6], 1)
+        # distance to its own fp16-rounded copy is tiny but not 0 (query is rounded too -> identical -> exactly 0)
+        assert d[0, 0] == 5 and s[0, 0] == 1.0
 
 
 def test_max_over_chunks_and_delete(gpu_required, score_oracle):
