@@ -64,7 +64,7 @@ enum b200_metric {
     B200_METRIC_PRENORMALIZED_ANGULAR = 0, /* distance = 1 - q.e           closeness = 1/(1+d) */
     B200_METRIC_ANGULAR = 1,               /* distance = acos(cos(q,e))    closeness = 1/(1+d) */
     B200_METRIC_DOTPRODUCT = 2,            /* distance = -q.e              closeness = q.e (raw) */
-    B200_METRIC_EUCLIDEAN = 3              /* distance = |q-e|             closeness = 1/(1+d) */
+    B200_METRIC_EUCLIDEAN = 3              /* distance = |q-e|             closeness = 1/(1+d)  (scan key 2 q.e - |e|^2) */
 };
 
 /* Create an empty row store of fp16[capacity_rows, dim] on `device` (grows on demand).

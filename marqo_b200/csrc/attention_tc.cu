@@ -8,6 +8,8 @@
 // (max, then exp2 / sum / bf16 P written to smem in the UMMA K-major swizzled layout), running-max rescale of the O
 // accumulator through tcgen05.ld/st, final 1/l scaling and the bf16 store.  112 KB smem + 256 TMEM columns per CTA ->
 // two CTAs per SM, so one CTA's softmax overlaps the other's MMAs.
+#include <mutex>
+
 #include "attention.cuh"
 #include "ptx.cuh"
 
@@ -424,16 +426,15 @@ void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W
                cudaStream_t stream) {
     if (B <= 0 || S <= 0) return;
     if (W != H * tc::HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);
-    static bool configured = false;
-    if (!configured) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tc::SMEM_BYTES));
         MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tc::SMEM_BYTES));
         MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_KEYLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)tc::SMEM_BYTES));
-        configured = true;
-    }
+    });
     // one tensor map over the packed [B*S, 3W] matrix serves Q, K and V tiles (64 columns x 128 rows, 128B swizzle);
     // rows past the end of the matrix are zero-filled, rows of the next sequence are masked by key index
     CUtensorMap tmap = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,

@@ -1,6 +1,7 @@
 #include "kernels.cuh"
 
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 namespace mb {
@@ -333,11 +334,10 @@ void clip_head(const float* x, int S, const int32_t* row_in_seq, const float* ga
                const float* proj, int n, int w, int E, int normalize, float* out, cudaStream_t s) {
     if (n <= 0) return;
     const size_t smem = ((size_t)w * HEAD_IMGS + (size_t)HEAD_IMGS * E) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static std::once_flag once;
+    std::call_once(once, [] {
         MB_CUDA(cudaFuncSetAttribute(clip_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
-    }
+    });
     if (smem > 160 * 1024) fail(B200_ERR_UNSUPPORTED, "clip_head: width %d / embed %d too large", w, E);
     clip_head_kernel<<<(n + HEAD_IMGS - 1) / HEAD_IMGS, 256, smem, s>>>(x, S, row_in_seq, gamma, beta, eps, proj, n, w, E,
                                                                         normalize, out);
