@@ -110,6 +110,14 @@ int b200_index_set_stream(b200_index* ix, void* cuda_stream, int use_external);
 /* Device time (ms, CUDA events on the handle's stream) of the scan / merge kernels of the last
  * search call; used by bench.py for the roofline numerator. */
 int b200_index_last_timing(b200_index* ix, float* scan_ms, float* merge_ms);
+/* Row-sharded corpora: every document number returned by this index is offset by `offset` (the global number of
+ * the shard's document 0), so per-shard results can be all-gathered and merged without a fix-up pass. */
+int b200_index_set_doc_offset(b200_index* ix, int32_t offset);
+/* Device-side merge of all-gathered per-shard results.  d_gathered holds, per shard, the packed block
+ * {int32 doc[nq,k] | int32 row[nq,k] | double score[nq,k]} (what b200_index_search_device writes when its three
+ * outputs point into one 16*nq*k-byte buffer); blocks are nq*k*16 bytes apart.  nshards*k <= 256. */
+int b200_topk_merge_device(b200_index* ix, const void* d_gathered, int nshards, int nq, int k, int32_t* d_out_doc,
+                           int32_t* d_out_row, double* d_out_score, int sync);
 /* Merge `nshards` per-shard result lists ([nshards, nq, k] each, host) into the global top-k
  * with the same total order; doc ids must already be global.  Used after the NCCL all-gather
  * of per-shard lists. */

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "b200_index_search_device": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int]),
     "b200_index_set_stream": (C.c_int, [_P, _P, C.c_int]),
     "b200_index_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "b200_index_set_doc_offset": (C.c_int, [_P, C.c_int32]),
+    "b200_topk_merge_device": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, C.c_int]),
     "b200_topk_merge": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "b200_index_save": (C.c_int, [_P, C.c_char_p]),
     "b200_index_load": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(_P)]),

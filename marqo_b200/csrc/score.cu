@@ -319,6 +319,7 @@ struct MergeParams {
     int k;
     int dim;
     int metric;
+    int doc_offset;  // added to every returned document number (global numbering of a row-sharded corpus)
     int sort_n;  // power of two >= num_lists * KP
     const float* in_score;
     const int32_t* in_row;
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeParams p) {
         for (int i = 0; i < p.k; ++i) {
             const size_t o = (size_t)q * p.k + i;
             if (i < n) {
-                p.out_doc[o] = sel_doc[i];
+                p.out_doc[o] = sel_doc[i] + p.doc_offset;
                 p.out_row[o] = sel_row[i];
                 p.out_score[o] = closeness_from_dot(sel_dot[i], p.metric);
             } else {
@@ -586,6 +587,81 @@ __global__ void next_bound_kernel(const float* cand_score, const int32_t* cand_r
     bound_row[q] = r >= 0 ? r : INT_MAX;
 }
 
+// Merge of all-gathered per-shard lists on the device: one warp per query, candidates strided over the lanes,
+// k rounds of warp arg-max under (score desc, doc asc).  Shard s's block: doc int32 [nq,k] | row int32 [nq,k] |
+// score f64 [nq,k] packed back to back (the layout b200_index_search_device writes when given one buffer).
+__global__ void merge_shards_kernel(const uint8_t* __restrict__ gathered, int nshards, int nq, int k, int32_t* out_doc,
+                                    int32_t* out_row, double* out_score) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const size_t blk = (size_t)nq * k * 16;
+    const int total = nshards * k;
+    constexpr int PER = 8;  // up to 256 candidates per query
+    double sc[PER];
+    int dc[PER], rw[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        sc[i] = -INFINITY;
+        dc[i] = INT_MAX;
+        rw[i] = -1;
+        if (c < total) {
+            const int s = c / k, e = c % k;
+            const uint8_t* base = gathered + (size_t)s * blk;
+            const int d = reinterpret_cast<const int32_t*>(base)[(size_t)q * k + e];
+            if (d >= 0) {
+                dc[i] = d;
+                rw[i] = reinterpret_cast<const int32_t*>(base + (size_t)nq * k * 4)[(size_t)q * k + e];
+                sc[i] = reinterpret_cast<const double*>(base + (size_t)nq * k * 8)[(size_t)q * k + e];
+            }
+        }
+    }
+    for (int r = 0; r < k; ++r) {
+        double bs = -INFINITY;
+        int bd = INT_MAX, bi = -1;
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (sc[i] > bs || (sc[i] == bs && dc[i] < bd)) {
+                bs = sc[i];
+                bd = dc[i];
+                bi = i;
+            }
+        int br = -1;
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (i == bi) br = rw[i];
+        int owner = lane;
+        for (int off = 16; off > 0; off >>= 1) {
+            const double os = __shfl_xor_sync(0xffffffffu, bs, off);
+            const int od = __shfl_xor_sync(0xffffffffu, bd, off);
+            const int orr = __shfl_xor_sync(0xffffffffu, br, off);
+            const int oo = __shfl_xor_sync(0xffffffffu, owner, off);
+            if (os > bs || (os == bs && od < bd)) {
+                bs = os;
+                bd = od;
+                br = orr;
+                owner = oo;
+            }
+        }
+        if (lane == 0) {
+            const size_t o = (size_t)q * k + r;
+            const bool ok = bd != INT_MAX;
+            out_doc[o] = ok ? bd : -1;
+            out_row[o] = ok ? br : -1;
+            out_score[o] = ok ? bs : -INFINITY;
+        }
+        if (lane == owner && bi >= 0) {   // retire the winner
+#pragma unroll
+            for (int i = 0; i < PER; ++i)
+                if (i == bi) {
+                    sc[i] = -INFINITY;
+                    dc[i] = INT_MAX;
+                }
+        }
+    }
+}
+
 __global__ void fill_empty_kernel(int32_t* out_doc, int32_t* out_row, double* out_score, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
@@ -610,6 +686,7 @@ struct b200_index {
     int64_t capacity = 0;
     int64_t n_rows = 0;
     bool has_docs = false;  // false while doc_of_row[i] == i for every row (identity fast path)
+    int32_t doc_offset = 0; // added to returned document numbers (shard -> global numbering)
     __half* corpus = nullptr;
     int32_t* doc_of_row = nullptr;
     float* row_n2 = nullptr;       // [capacity] squared norms (euclidean metric only)
@@ -821,6 +898,7 @@ void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_
     mp.k = k;
     mp.dim = ix->dim;
     mp.metric = ix->metric;
+    mp.doc_offset = ix->doc_offset;
     int sort_n = 32;
     while (sort_n < grid * KP) sort_n <<= 1;
     mp.sort_n = sort_n;
@@ -1105,6 +1183,30 @@ int b200_index_set_stream(b200_index* ix, void* cuda_stream, int use_external) {
         DeviceGuard g(ix->device);
         MB_CUDA(cudaStreamSynchronize(ix->stream));
         ix->stream = use_external ? reinterpret_cast<cudaStream_t>(cuda_stream) : ix->own_stream;
+    });
+}
+
+int b200_index_set_doc_offset(b200_index* ix, int32_t offset) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix != nullptr, "index is NULL");
+        MB_CHECK_ARG(offset >= 0, "offset must be >= 0");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        ix->doc_offset = offset;
+    });
+}
+
+int b200_topk_merge_device(b200_index* ix, const void* d_gathered, int nshards, int nq, int k, int32_t* d_out_doc,
+                           int32_t* d_out_row, double* d_out_score, int sync) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix && d_gathered && d_out_doc && d_out_row && d_out_score, "NULL argument");
+        MB_CHECK_ARG(nshards > 0 && nq > 0 && k > 0, "nshards, nq, k must be positive");
+        if (nshards * k > 256) fail(B200_ERR_UNSUPPORTED, "device merge handles up to 256 candidates per query");
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        merge_shards_kernel<<<(nq + 3) / 4, 128, 0, ix->stream>>>(reinterpret_cast<const uint8_t*>(d_gathered), nshards, nq,
+                                                                k, d_out_doc, d_out_row, d_out_score);
+        MB_CUDA(cudaGetLastError());
+        if (sync) MB_CUDA(cudaStreamSynchronize(ix->stream));
     });
 }
 

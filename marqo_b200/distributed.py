@@ -63,11 +63,11 @@ class ShardedRowStore:
 
     def add_local(self, vecs, local_doc_ids: Optional[Sequence[int]], doc_base: int) -> None:
         self.doc_base = int(doc_base)
+        self.store.set_doc_offset(self.doc_base)     # the engine returns global document numbers directly
         self.store.add(vecs, local_doc_ids)
 
     def search(self, queries, k: int):
-        doc, row, score = self.store.search(queries, k)
-        gdoc = np.where(doc >= 0, doc + self.doc_base, -1).astype(np.int32)
+        gdoc, row, score = self.store.search(queries, k)
         if self.world == 1:
             return gdoc, row, score
         return allgather_topk(gdoc, row, score, self.group, self.device)

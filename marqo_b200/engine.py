@@ -115,6 +115,15 @@ class RowStore:
         N.check(self._lib.b200_index_set_stream(self._handle(), C.c_void_p(cuda_stream or 0),
                                                 0 if cuda_stream is None else 1))
 
+    def set_doc_offset(self, offset: int) -> None:
+        N.check(self._lib.b200_index_set_doc_offset(self._handle(), int(offset)))
+
+    def merge_shards_device(self, d_gathered_ptr: int, nshards: int, nq: int, k: int, d_doc_ptr: int, d_row_ptr: int,
+                            d_score_ptr: int, sync: bool = True) -> None:
+        N.check(self._lib.b200_topk_merge_device(self._handle(), C.c_void_p(d_gathered_ptr), nshards, nq, k,
+                                                 C.c_void_p(d_doc_ptr), C.c_void_p(d_row_ptr), C.c_void_p(d_score_ptr),
+                                                 1 if sync else 0))
+
     def last_timing(self) -> Tuple[float, float]:
         a, b = C.c_float(0), C.c_float(0)
         N.check(self._lib.b200_index_last_timing(self._handle(), C.byref(a), C.byref(b)))
