@@ -258,90 +258,96 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
     return t;
 }
 
-// CLIP head: 4 images per CTA so that every element of the fp32 projection matrix read from L2 feeds 4 FMAs.
+// CLIP head in three small kernels with enough parallelism to be latency-free:
+//   (1) head_ln_kernel      one warp per image: gather the pooled token row, LayerNorm -> pooled fp32 [n, w]
+//   (2) head_proj_kernel    grid (n/4, E/64): 4 images x 64 outputs per CTA, K split over 4 thread groups
+//   (3) head_norm_kernel    one warp per image: L2 normalise (no epsilon, abstract_clip_model.py:83-85)
 constexpr int HEAD_IMGS = 4;
+constexpr int HEAD_COLS = 64;
 
-__global__ void __launch_bounds__(256) clip_head_kernel(const float* __restrict__ x, int S, const int32_t* __restrict__ row_in_seq,
-                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        float eps, const float* __restrict__ proj, int n, int w, int E,
-                                                        int normalize, float* __restrict__ out) {
-    extern __shared__ float sh[];          // pooledT [w][8]  +  res [8][E]
-    __shared__ float red[8][HEAD_IMGS];
-    float* pooledT = sh;
-    float* res = sh + (size_t)w * HEAD_IMGS;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) head_ln_kernel(const float* __restrict__ x, int S, const int32_t* __restrict__ row_in_seq,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float eps, int n, int w, float* __restrict__ pooled) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= n) return;
+    const int r = row_in_seq ? row_in_seq[b] : 0;
+    const float* src = x + ((long long)b * S + r) * w;
+    float s = 0.f;
+    for (int i = lane; i < w; i += 32) s += src[i];
+    const float mean = warp_sum(s) / (float)w;
+    float q = 0.f;
+    for (int i = lane; i < w; i += 32) {
+        const float d = src[i] - mean;
+        q += d * d;
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)w + eps);
+    for (int i = lane; i < w; i += 32) pooled[(long long)b * w + i] = (src[i] - mean) * rstd * gamma[i] + beta[i];
+}
+
+__global__ void __launch_bounds__(256) head_proj_kernel(const float* __restrict__ pooled, const float* __restrict__ proj, int n,
+                                                        int w, int E, float* __restrict__ out) {
+    __shared__ float part[4][HEAD_IMGS][HEAD_COLS];
+    extern __shared__ float s_pool[];   // [HEAD_IMGS][w]
     const int b0 = blockIdx.x * HEAD_IMGS;
-    if (warp < HEAD_IMGS) {   // LayerNorm: warp k normalises image b0 + k (two-pass, like layernorm_kernel)
-        const int b = b0 + warp;
-        if (b < n) {
-            const int r = row_in_seq ? row_in_seq[b] : 0;
-            const float* src = x + ((long long)b * S + r) * w;
-            float s = 0.f;
-            for (int i = lane; i < w; i += 32) s += src[i];
-            const float mean = warp_sum(s) / (float)w;
-            float q = 0.f;
-            for (int i = lane; i < w; i += 32) {
-                const float d = src[i] - mean;
-                q += d * d;
-            }
-            const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)w + eps);
-            for (int i = lane; i < w; i += 32) pooledT[i * HEAD_IMGS + warp] = (src[i] - mean) * rstd * gamma[i] + beta[i];
-        } else {
-            for (int i = lane; i < w; i += 32) pooledT[i * HEAD_IMGS + warp] = 0.f;
-        }
+    const int e = blockIdx.y * HEAD_COLS + (threadIdx.x & (HEAD_COLS - 1));
+    const int slice = threadIdx.x >> 6;   // 4 K-slices
+    for (int i = threadIdx.x; i < HEAD_IMGS * w; i += 256) {
+        const int k = i / w, c = i - k * w;
+        s_pool[i] = b0 + k < n ? pooled[(long long)(b0 + k) * w + c] : 0.f;
     }
     __syncthreads();
-    float ss[HEAD_IMGS];
+    float acc[HEAD_IMGS];
 #pragma unroll
-    for (int k = 0; k < HEAD_IMGS; ++k) ss[k] = 0.f;
-    for (int e = threadIdx.x; e < E; e += 256) {
-        float acc[HEAD_IMGS];
-#pragma unroll
-        for (int k = 0; k < HEAD_IMGS; ++k) acc[k] = 0.f;
+    for (int k = 0; k < HEAD_IMGS; ++k) acc[k] = 0.f;
+    const int i0 = slice * (w / 4), i1 = i0 + w / 4;
+    if (e < E) {
 #pragma unroll 8
-        for (int i = 0; i < w; ++i) {
+        for (int i = i0; i < i1; ++i) {
             const float pj = __ldg(proj + (long long)i * E + e);
-            const float4 a = *reinterpret_cast<const float4*>(pooledT + i * HEAD_IMGS);
-            acc[0] = fmaf(a.x, pj, acc[0]);
-            acc[1] = fmaf(a.y, pj, acc[1]);
-            acc[2] = fmaf(a.z, pj, acc[2]);
-            acc[3] = fmaf(a.w, pj, acc[3]);
-        }
 #pragma unroll
-        for (int k = 0; k < HEAD_IMGS; ++k) {
-            res[k * E + e] = acc[k];
-            ss[k] += acc[k] * acc[k];
+            for (int k = 0; k < HEAD_IMGS; ++k) acc[k] = fmaf(s_pool[k * w + i], pj, acc[k]);
         }
     }
 #pragma unroll
-    for (int k = 0; k < HEAD_IMGS; ++k) {
-        const float v = warp_sum(ss[k]);
-        if (lane == 0) red[warp][k] = v;
-    }
+    for (int k = 0; k < HEAD_IMGS; ++k) part[slice][k][threadIdx.x & (HEAD_COLS - 1)] = acc[k];
     __syncthreads();
-    for (int k = 0; k < HEAD_IMGS; ++k) {
-        const int b = b0 + k;
-        if (b >= n) break;
-        float t = 0.f;
+    if (slice == 0 && e < E) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) t += red[i][k];
-        const float nrm = sqrtf(t);
-        for (int e = threadIdx.x; e < E; e += 256) out[(long long)b * E + e] = normalize ? res[k * E + e] / nrm : res[k * E + e];
+        for (int k = 0; k < HEAD_IMGS; ++k)
+            if (b0 + k < n) {
+                const int c = threadIdx.x & (HEAD_COLS - 1);
+                // fixed order: the result does not depend on scheduling
+                out[(long long)(b0 + k) * E + e] = ((part[0][k][c] + part[1][k][c]) + part[2][k][c]) + part[3][k][c];
+            }
     }
 }
 
+__global__ void __launch_bounds__(256) head_norm_kernel(float* __restrict__ out, int n, int E) {
+    const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= n) return;
+    float* row = out + (long long)b * E;
+    float ss = 0.f;
+    for (int i = lane; i < E; i += 32) ss += row[i] * row[i];
+    const float nrm = sqrtf(warp_sum(ss));
+    for (int i = lane; i < E; i += 32) row[i] = row[i] / nrm;
+}
+
 void clip_head(const float* x, int S, const int32_t* row_in_seq, const float* gamma, const float* beta, float eps,
-               const float* proj, int n, int w, int E, int normalize, float* out, cudaStream_t s) {
+               const float* proj, int n, int w, int E, int normalize, float* out, float* pooled_ws, cudaStream_t s) {
     if (n <= 0) return;
-    const size_t smem = ((size_t)w * HEAD_IMGS + (size_t)HEAD_IMGS * E) * sizeof(float);
-    static std::once_flag once;
-    std::call_once(once, [] {
-        MB_CUDA(cudaFuncSetAttribute(clip_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    });
-    if (smem > 160 * 1024) fail(B200_ERR_UNSUPPORTED, "clip_head: width %d / embed %d too large", w, E);
-    clip_head_kernel<<<(n + HEAD_IMGS - 1) / HEAD_IMGS, 256, smem, s>>>(x, S, row_in_seq, gamma, beta, eps, proj, n, w, E,
-                                                                        normalize, out);
+    if (w % 4 != 0 || (size_t)HEAD_IMGS * w * sizeof(float) > 40 * 1024)
+        fail(B200_ERR_UNSUPPORTED, "clip_head: width %d unsupported", w);
+    head_ln_kernel<<<(n + 7) / 8, 256, 0, s>>>(x, S, row_in_seq, gamma, beta, eps, n, w, pooled_ws);
     MB_CUDA(cudaGetLastError());
+    const dim3 grid((n + HEAD_IMGS - 1) / HEAD_IMGS, (E + HEAD_COLS - 1) / HEAD_COLS);
+    head_proj_kernel<<<grid, 256, (size_t)HEAD_IMGS * w * sizeof(float), s>>>(pooled_ws, proj, n, w, E, out);
+    MB_CUDA(cudaGetLastError());
+    if (normalize) {
+        head_norm_kernel<<<(n + 7) / 8, 256, 0, s>>>(out, n, E);
+        MB_CUDA(cudaGetLastError());
+    }
 }
 
 __global__ void __launch_bounds__(256) bert_head_kernel(const float* __restrict__ x, const int32_t* __restrict__ kv_len, int S,

@@ -33,8 +33,9 @@ void bert_embed_ln(const int32_t* ids, const int32_t* mask, const float* word, c
 
 // CLIP head: for image b take token row (b * S + row_in_seq[b]) (row_in_seq NULL -> 0), LayerNorm it, multiply by
 // proj [w, E] (fp32), optionally divide by the L2 norm (no epsilon: abstract_clip_model.py:83-85).
+// pooled_ws: fp32 workspace [n, w].
 void clip_head(const float* x, int S, const int32_t* row_in_seq, const float* gamma, const float* beta, float eps,
-               const float* proj, int n, int w, int E, int normalize, float* out, cudaStream_t s);
+               const float* proj, int n, int w, int E, int normalize, float* out, float* pooled_ws, cudaStream_t s);
 
 // BERT head: masked mean over the first kv_len[b] tokens (pool == 0) or the [CLS] row (pool == 1), then
 // x / max(|x|, 1e-12) if normalize (F.normalize, hugging_face_model.py:194-195).

@@ -71,6 +71,7 @@ struct b200_model {
     __nv_bfloat16 *h = nullptr, *qkv = nullptr, *o = nullptr, *u = nullptr, *patches = nullptr;
     int32_t *aux = nullptr;           // [max_batch] eot index / kv_len
     float* out_dev = nullptr;         // [max_batch, embed]
+    float* pooled = nullptr;          // [max_batch, width] LayerNorm-ed pooled rows (CLIP heads)
     void* in_dev = nullptr;           // staging for host inputs
     size_t in_dev_bytes = 0;
     uint8_t* resized = nullptr;       // [max_batch, S, S, 3]
@@ -111,6 +112,7 @@ void model_free(b200_model* m) {
     cudaFree(m->patches);
     cudaFree(m->aux);
     cudaFree(m->out_dev);
+    cudaFree(m->pooled);
     cudaFree(m->in_dev);
     cudaFree(m->resized);
     if (m->ev0) cudaEventDestroy(m->ev0);
@@ -350,8 +352,8 @@ void forward_images(b200_model* m, Counter& c, const uint8_t* u8, const float* f
     c.n += 3;
     run_clip_blocks(m, c, T, n, T.tokens, attention::MASK_NONE);
     kernels::clip_head(m->x, T.tokens, nullptr, T.ln_out_w, T.ln_out_b, 1e-5f, T.proj, n, w, m->desc.embed_dim, normalize,
-                       d_out, m->stream);
-    c.n += 1;
+                       d_out, m->pooled, m->stream);
+    c.n += 3;
 }
 
 void forward_tokens(b200_model* m, Counter& c, const int32_t* d_ids, const int32_t* d_mask, int n, int S, int normalize,
@@ -363,8 +365,8 @@ void forward_tokens(b200_model* m, Counter& c, const int32_t* d_ids, const int32
         c.n += 1;
         run_clip_blocks(m, c, T, n, S, attention::MASK_CAUSAL);
         kernels::clip_head(m->x, S, m->aux, T.ln_out_w, T.ln_out_b, 1e-5f, T.proj, n, w, m->desc.embed_dim, normalize,
-                           d_out, m->stream);
-        c.n += 1;
+                           d_out, m->pooled, m->stream);
+        c.n += 3;
     } else {
         kernels::bert_embed_ln(d_ids, d_mask, T.tok, T.pos, T.type0, T.emb_ln_w, T.emb_ln_b, 1e-12f, n, S, w, T.d.vocab,
                                m->x, m->h, m->aux, m->stream);
@@ -595,6 +597,7 @@ int b200_model_finalize(b200_model* m) {
         dev_alloc((void**)&m->u, (size_t)m->max_tokens * max_mlp * 2);
         dev_alloc((void**)&m->aux, (size_t)m->desc.max_batch * 4);
         dev_alloc((void**)&m->out_dev, (size_t)m->desc.max_batch * E * 4);
+        dev_alloc((void**)&m->pooled, (size_t)m->desc.max_batch * max_w * 4);
         MB_CUDA(cudaStreamSynchronize(m->stream));
         m->finalized = true;
     });
