@@ -129,7 +129,7 @@ template <int MASK>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ qkv,
                     __nv_bfloat16* __restrict__ out, int S, int W, const int32_t* __restrict__ kv_len, float scale_log2e,
-                    int s_main) {
+                    int s_main, int inline_tail_rows) {
     // Keys [0, s_main) go through the tensor cores in blocks of 128; the few keys [s_main, S) of a sequence length
     // such as 257 = 2 * 128 + 1 (ViT class token) are folded in on the CUDA cores in the epilogue instead of paying
     // for a whole extra 128-wide block.
@@ -193,6 +193,118 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                 ptx::tma_load_2d(dst, &tmap, &kv_full[st], W + h * HD, row_base + j * BKV, ptx::kEvictLast);
                 ptx::tma_load_2d(dst + KV_TILE_BYTES, &tmap, &kv_full[st], 2 * W + h * HD, row_base + j * BKV,
                                  ptx::kEvictLast);
+            }
+        }
+        __syncwarp();
+        // ---------------------------------------------------------------- remainder query rows (S = k*128 + r)
+        // The producer warp is idle once the loads are issued: in the CTA of the last full query block it computes
+        // the r <= 8 remainder rows against the K / V tiles while they sit in shared memory (the host only enables
+        // this when all key blocks fit the ring without reuse), instead of a second kernel re-reading K and V from HBM.
+        if (inline_tail_rows > 0 && blockIdx.x == gridDim.x - 1) {
+            const size_t ld = (size_t)3 * W;
+            for (int tr = 0; tr < inline_tail_rows; ++tr) {
+                const int trow = s_main + tr;
+                int tlimit = len;                               // keys >= tlimit are masked for this row
+                if (MASK == MASK_CAUSAL) tlimit = min(tlimit, trow + 1);
+                const __nv_bfloat16* qrow_p = qkv + ((size_t)row_base + trow) * ld + h * HD;
+                float qf[HD];
+                {
+                    const uint4* qp = reinterpret_cast<const uint4*>(qrow_p);
+#pragma unroll
+                    for (int u = 0; u < HD / 8; ++u) {
+                        const uint4 t4 = __ldg(qp + u);
+                        const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+                            qf[8 * u + 2 * e] = f2.x * scale_log2e;
+                            qf[8 * u + 2 * e + 1] = f2.y * scale_log2e;
+                        }
+                    }
+                }
+                const float2 qpair = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(qrow_p)[lane]);
+                float m_t = -INFINITY, l_t = 0.f, ox = 0.f, oy = 0.f;
+                for (int j = 0; j < nkb; ++j) {
+                    const int st = j & 1;
+                    ptx::mbar_wait(&kv_full[st], (j >> 1) & 1);
+                    const uint8_t* kt = sKV + (size_t)st * 2 * KV_TILE_BYTES;
+                    const uint8_t* vt = kt + KV_TILE_BYTES;
+                    float sc[4];
+                    float bm = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int key = lane + 32 * i;   // row & 7 == lane & 7: the 8 swizzled units spread over the banks
+                        float acc = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const uint4 k4 = *reinterpret_cast<const uint4*>(kt + key * 128 + ((u ^ (key & 7)) << 4));
+                            const uint32_t w4[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
+                                acc = fmaf(qf[8 * u + 2 * e], f2.x, acc);
+                                acc = fmaf(qf[8 * u + 2 * e + 1], f2.y, acc);
+                            }
+                        }
+                        const int gkey = j * BKV + key;
+                        sc[i] = (gkey < tlimit && gkey < s_main) ? acc : -INFINITY;
+                        bm = fmaxf(bm, sc[i]);
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, off));
+                    const float m_new = fmaxf(m_t, bm);
+                    const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+                    const float alpha = ex2(m_t - m_safe);
+                    float pb[4];
+                    float ls = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float pe = sc[i] == -INFINITY ? 0.f : ex2(sc[i] - m_safe);
+                        ls += pe;
+                        pb[i] = __bfloat162float(__float2bfloat16_rn(pe));   // same P rounding as the MMA path
+                    }
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
+                    l_t = l_t * alpha + ls;
+                    ox *= alpha;
+                    oy *= alpha;
+                    m_t = m_new;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+#pragma unroll 8
+                        for (int src = 0; src < 32; ++src) {
+                            const int key = src + 32 * i;
+                            const float pk = __shfl_sync(0xffffffffu, pb[i], src);
+                            const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(
+                                vt + key * 128 + (((lane >> 2) ^ (key & 7)) << 4) + (lane & 3) * 4);
+                            const float2 vf = __bfloat1622float2(v2);
+                            ox = fmaf(pk, vf.x, ox);
+                            oy = fmaf(pk, vf.y, oy);
+                        }
+                    }
+                }
+                // remainder keys from global memory (lanes over the 64 dims, warp-reduced dot)
+                for (int key = s_main; key < tlimit; ++key) {
+                    const float2 kf = __bfloat1622float2(
+                        reinterpret_cast<const __nv_bfloat162*>(qkv + ((size_t)row_base + key) * ld + W + h * HD)[lane]);
+                    const float2 vf = __bfloat1622float2(
+                        reinterpret_cast<const __nv_bfloat162*>(qkv + ((size_t)row_base + key) * ld + 2 * W + h * HD)[lane]);
+                    float sd = qpair.x * kf.x + qpair.y * kf.y;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, off);
+                    const float scv = sd * scale_log2e;
+                    const float m_new = fmaxf(m_t, scv);
+                    const float alpha = ex2(m_t - m_new);
+                    const float pe = ex2(scv - m_new);
+                    const float pbv = __bfloat162float(__float2bfloat16_rn(pe));
+                    l_t = l_t * alpha + pe;
+                    ox = fmaf(ox, alpha, pbv * vf.x);
+                    oy = fmaf(oy, alpha, pbv * vf.y);
+                    m_t = m_new;
+                }
+                const float inv_t = l_t > 0.f ? 1.f / l_t : 0.f;
+                reinterpret_cast<__nv_bfloat162*>(out + ((size_t)row_base + trow) * W + h * HD)[lane] =
+                    __floats2bfloat162_rn(ox * inv_t, oy * inv_t);
             }
         }
     } else if (warp == 1) {
@@ -447,27 +559,30 @@ void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W
     const int q_blocks = tail ? S / tc::BQ : (S + tc::BQ - 1) / tc::BQ;
     const dim3 grid(q_blocks, H, B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;
-    const int tail_total = tail ? B * H * rem : 0;
+    // remainder query rows inside the main kernel when every key block fits the 2-stage ring without reuse
+    const bool inline_tail = tail && s_main / tc::BKV <= tc::KV_STAGES;
+    const int inline_rows = inline_tail ? rem : 0;
+    const int tail_total = (tail && !inline_tail) ? B * H * rem : 0;
     switch (mask) {
         case MASK_NONE:
             tc::attention_tc_kernel<MASK_NONE><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, kv_len,
-                                                                                             scale_log2e, s_main);
-            if (tail)
+                                                                                             scale_log2e, s_main, inline_rows);
+            if (tail_total > 0)
                 tc::attention_tail_rows_kernel<MASK_NONE><<<(tail_total + 3) / 4, 128, 0, stream>>>(
                     qkv, out, S, W, H, s_main, kv_len, scale_log2e, tail_total);
             break;
         case MASK_CAUSAL:
             tc::attention_tc_kernel<MASK_CAUSAL><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, kv_len,
-                                                                                               scale_log2e, s_main);
-            if (tail)
+                                                                                               scale_log2e, s_main, inline_rows);
+            if (tail_total > 0)
                 tc::attention_tail_rows_kernel<MASK_CAUSAL><<<(tail_total + 3) / 4, 128, 0, stream>>>(
                     qkv, out, S, W, H, s_main, kv_len, scale_log2e, tail_total);
             break;
         case MASK_KEYLEN:
             if (!kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
             tc::attention_tc_kernel<MASK_KEYLEN><<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, kv_len,
-                                                                                               scale_log2e, s_main);
-            if (tail)
+                                                                                               scale_log2e, s_main, inline_rows);
+            if (tail_total > 0)
                 tc::attention_tail_rows_kernel<MASK_KEYLEN><<<(tail_total + 3) / 4, 128, 0, stream>>>(
                     qkv, out, S, W, H, s_main, kv_len, scale_log2e, tail_total);
             break;
