@@ -225,15 +225,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
     }
 }
 
-void launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
-            cudaStream_t stream) {
-    if (B <= 0 || S <= 0) return;
+int launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+           cudaStream_t stream) {
+    if (B <= 0 || S <= 0) return 0;
     // Sequences of at least one full 128-row tile run on the tcgen05 kernel (attention_tc.cu).  Shorter ones
     // (ViT-B-32: 50 tokens, CLIP text: 77) would leave most of a 128 x 128 tile masked; the 64-row warp-level
     // kernel below wastes far less on them (measured on B200: 0.33 ms vs 0.72 ms per ViT-B-32 step).
     if (S >= 128) {
-        launch_tc(qkv, out, B, S, W, H, mask, kv_len, stream);
-        return;
+        return launch_tc(qkv, out, B, S, W, H, mask, kv_len, stream);
     }
     if (W != H * HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);
     const dim3 grid((S + BQ - 1) / BQ, H, B);
@@ -253,6 +252,7 @@ void launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, i
             fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);
     }
     MB_CUDA(cudaGetLastError());
+    return 1;
 }
 
 }  // namespace attention

@@ -12,12 +12,13 @@ enum Mask { MASK_NONE = 0, MASK_CAUSAL = 1, MASK_KEYLEN = 2 };
 
 // qkv: bf16 [B*S, 3*W] rows = tokens, columns = [q | k | v], head h occupies columns h*64..h*64+63 of each part.
 // out: bf16 [B*S, W].  kv_len: int32 [B] valid key count per sequence (MASK_KEYLEN only).
-void launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
-            cudaStream_t stream);
+// Returns the number of kernels launched.
+int launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+           cudaStream_t stream);
 
 // tcgen05 / TMEM implementation (attention_tc.cu)
-void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
-               cudaStream_t stream);
+int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+              cudaStream_t stream);
 
 }  // namespace attention
 }  // namespace mb

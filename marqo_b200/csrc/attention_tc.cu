@@ -534,9 +534,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
 
 }  // namespace tc
 
-void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
-               cudaStream_t stream) {
-    if (B <= 0 || S <= 0) return;
+int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+              cudaStream_t stream) {
+    if (B <= 0 || S <= 0) return 0;
     if (W != H * tc::HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);
     static std::once_flag once;
     std::call_once(once, [] {
@@ -590,6 +590,7 @@ void launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W
             fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);
     }
     MB_CUDA(cudaGetLastError());
+    return tail_total > 0 ? 2 : 1;
 }
 
 }  // namespace attention

@@ -249,9 +249,9 @@ void linear(b200_model* m, Counter& c, const __nv_bfloat16* A, int M, int K, con
     ++c.n;
 }
 
-void attend(b200_model* m, int B, int S, int w, int heads, int mask_mode, const int32_t* kv_len) {
+void attend(b200_model* m, Counter& c, int B, int S, int w, int heads, int mask_mode, const int32_t* kv_len) {
     ProfScope ps(m, 1);
-    attention::launch(m->qkv, m->o, B, S, w, heads, mask_mode, kv_len, m->stream);
+    c.n += attention::launch(m->qkv, m->o, B, S, w, heads, mask_mode, kv_len, m->stream);
 }
 
 // Pre-LN residual blocks (open_clip ResidualAttentionBlock).
@@ -265,7 +265,7 @@ void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, i
         e1.out = m->qkv;
         e1.ldo = 3 * w;
         linear(m, c, m->h, M, w, L.w_qkv, 3 * w, e1);
-        attend(m, B, S, w, T.d.heads, mask_mode, nullptr);
+        attend(m, c, B, S, w, T.d.heads, mask_mode, nullptr);
         gemm::Epilogue e2;
         e2.bias = L.b_o;
         e2.residual = m->x;
@@ -289,7 +289,7 @@ void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, i
         e4.ldo = w;
         e4.out_fp32 = 1;
         linear(m, c, m->u, M, mlp, L.w_proj, w, e4);
-        c.n += 3;
+        c.n += 2;   // the two LayerNorm launches
     }
 }
 
@@ -303,7 +303,7 @@ void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
         e1.out = m->qkv;
         e1.ldo = 3 * w;
         linear(m, c, m->h, M, w, L.w_qkv, 3 * w, e1);
-        attend(m, B, S, w, T.d.heads, attention::MASK_KEYLEN, m->aux);
+        attend(m, c, B, S, w, T.d.heads, attention::MASK_KEYLEN, m->aux);
         gemm::Epilogue e2;
         e2.bias = L.b_o;
         e2.residual = m->x;
@@ -328,7 +328,7 @@ void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
         e4.out_fp32 = 1;
         linear(m, c, m->u, M, mlp, L.w_proj, w, e4);
         kernels::layernorm(m->x, w, L.ln2_w, L.ln2_b, eps, M, w, m->x, m->h, m->stream);
-        c.n += 3;
+        c.n += 2;   // the two LayerNorm launches
     }
 }
 
