@@ -104,6 +104,30 @@ int b200_index_search(b200_index* ix, const float* q, int nq, int k, int32_t* ou
  * stream unless sync != 0. */
 int b200_index_search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_out_doc,
                              int32_t* d_out_row, double* d_out_score, int sync);
+
+/* Score modifiers.  Per-document numeric attributes: the `marqo__score_modifiers`
+ * tensor<double>(p{}) field every document is fed with
+ * (src/marqo/core/unstructured_vespa_index/unstructured_document.py:25,110-125;
+ * src/marqo/core/semi_structured_vespa_index/semi_structured_document.py:23,104-117).  The host maps each
+ * attribute NAME to a column number in [0, B200_MAX_ATTRIBUTE_COLUMNS).  values == NULL removes the cells (the
+ * document no longer has the attribute); column == -1 with values == NULL removes the documents' cells in every
+ * column (document overwritten or deleted).  Document numbers are LOCAL (before b200_index_set_doc_offset). */
+#define B200_MAX_ATTRIBUTE_COLUMNS 64
+int b200_index_set_attributes(b200_index* ix, int column, const int32_t* doc_ids, const double* values, int64_t n);
+/* b200_index_search with the rank-profile function
+ *   modify(score, mult_weights, add_weights) =
+ *       if(count(mult_weights * attr) == 0, 1, reduce(mult_weights * attr, prod)) * score + reduce(add_weights * attr, sum)
+ * (src/marqo/core/unstructured_vespa_index/unstructured_vespa_schema.py:266-271, applied at :225-230) evaluated
+ * inside the scan, before top-k; `score` = closeness of the document's best chunk.  The sparse products run over the
+ * attribute cells a document has.  mult_cols/mult_w and add_cols/add_w are the query tensors
+ * `marqo__mult_weights_tensor` / `marqo__add_weights_tensor` (src/marqo/core/vespa_index/vespa_index.py:124-150;
+ * src/marqo/core/constants.py:22-27) as (column, weight) lists, at most 16 each, evaluated in list order in fp64.
+ * out_score is the MODIFIED score; order (score desc, doc asc).  B200_ERR_UNSUPPORTED when some document's
+ * multiplier is negative on an index with explicit document ids (best chunk != best modified chunk). */
+int b200_index_search_modified(b200_index* ix, const float* q, int nq, int k, const int32_t* mult_cols,
+                               const double* mult_w, int n_mult, const int32_t* add_cols, const double* add_w, int n_add,
+                               int32_t* out_doc, int32_t* out_row, double* out_score);
+
 /* use_external != 0: run this handle's work on the caller's CUDA stream (a cudaStream_t, e.g. torch's current
  * stream; the value 0 is the legacy default stream).  use_external == 0 restores the handle's private stream. */
 int b200_index_set_stream(b200_index* ix, void* cuda_stream, int use_external);
@@ -209,6 +233,22 @@ int b200_model_last_timing(b200_model* m, float* ms, int* launches);
  * src/marqo/core/inference/tensor_fields_container.py:355-365:
  * out = mean_i(w_i * v_i); if normalize and |out| > 0: out /= |out|.  fp64 arithmetic. */
 int b200_fuse_vectors(const double* vecs, const double* weights, int n, int dim, int normalize, double* out);
+
+/* Recommender interpolation: src/marqo/core/utils/vector_interpolation.py —
+ * Lerp.interpolate :49-88 (sum_i (w_i / sum w) v_i), Nlerp.interpolate :91-119 (Lerp, then / |.|),
+ * Slerp hierarchical :121-193,211-237.  vecs: fp64 [n, dim] host; out: fp64 [dim].  Host-side fp64 arithmetic in
+ * the reference's order (these are <= a few dozen vectors per recommend call, src/marqo/core/search/recommender.py:88).
+ * On the reference's error conditions returns B200_ERR_INVALID_ARG and stores which one in *out_error_kind so the
+ * binding can raise ZeroSumWeightsError / ZeroMagnitudeVectorError / ValueError like the reference. */
+enum b200_interp_method { B200_INTERP_LERP = 0, B200_INTERP_NLERP = 1, B200_INTERP_SLERP = 2 };
+enum b200_interp_error {
+    B200_INTERP_OK = 0,
+    B200_INTERP_ZERO_SUM_WEIGHTS = 1, /* ZeroSumWeightsError      (:12, :74-77, :226-228) */
+    B200_INTERP_ZERO_MAGNITUDE = 2,   /* ZeroMagnitudeVectorError (:16, :113-116) */
+    B200_INTERP_ZERO_LENGTH = 3       /* ValueError               (:171-173) */
+};
+int b200_interpolate_vectors(const double* vecs, const double* weights, int n, int dim, int method, double* out,
+                             int* out_error_kind);
 
 /* ===================================================================================== */
 /* Diagnostics: run ONE kernel of the encoder on host data (used by the kernel-level     */

@@ -17,6 +17,8 @@ METRIC_PRENORMALIZED_ANGULAR, METRIC_ANGULAR, METRIC_DOTPRODUCT, METRIC_EUCLIDEA
 ARCH_CLIP, ARCH_BERT = 0, 1
 ACT_GELU, ACT_QUICKGELU = 0, 1
 POOL_MEAN, POOL_CLS = 0, 1
+MAX_ATTRIBUTE_COLUMNS = 64
+MAX_MODIFIER_TERMS = 16
 
 
 class NativeError(RuntimeError):
@@ -58,6 +60,8 @@ _SIGNATURES = {
     "b200_index_get_row": (C.c_int, [_P, C.c_int64, _P]),
     "b200_index_search": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P]),
     "b200_index_search_device": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int]),
+    "b200_index_set_attributes": (C.c_int, [_P, C.c_int, _P, _P, C.c_int64]),
+    "b200_index_search_modified": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, _P, C.c_int, _P, _P, _P]),
     "b200_index_set_stream": (C.c_int, [_P, _P, C.c_int]),
     "b200_index_last_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "b200_index_set_doc_offset": (C.c_int, [_P, C.c_int32]),
@@ -83,6 +87,7 @@ _SIGNATURES = {
     "b200_debug_layernorm": (C.c_int, [C.c_int, _P, _P, _P, C.c_float, C.c_int, C.c_int, _P]),
     "b200_debug_resize": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "b200_fuse_vectors": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P]),
+    "b200_interpolate_vectors": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.POINTER(C.c_int)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,3 +1,6 @@
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 
 #include <mutex>
@@ -95,6 +98,109 @@ int b200_fuse_vectors(const double* vecs, const double* weights, int n, int dim,
             if (nrm > 0.0)
                 for (int d = 0; d < dim; ++d) out[d] /= nrm;
         }
+    });
+}
+
+namespace {
+
+// One SLERP step of the reference (vector_interpolation.py:160-195): angle from the normalised dot product, linear
+// fallback for co-linear inputs.  Returns false when either input has zero length.
+bool slerp_pair(const double* v0, const double* v1, double t, int dim, double* out) {
+    double dot = 0.0, n0 = 0.0, n1 = 0.0;
+    for (int i = 0; i < dim; ++i) {
+        dot += v0[i] * v1[i];
+        n0 += v0[i] * v0[i];
+        n1 += v1[i] * v1[i];
+    }
+    n0 = sqrt(n0);
+    n1 = sqrt(n1);
+    if (n0 == 0.0 || n1 == 0.0) return false;
+    double c = dot / (n0 * n1);
+    c = c > 1.0 ? 1.0 : (c < -1.0 ? -1.0 : c);
+    const double theta = acos(c);
+    const double st = sin(theta);
+    if (st == 0.0) {
+        for (int i = 0; i < dim; ++i) out[i] = (1.0 - t) * v0[i] + t * v1[i];
+        return true;
+    }
+    const double a = sin((1.0 - t) * theta) / st, b = sin(t * theta) / st;
+    for (int i = 0; i < dim; ++i) out[i] = a * v0[i] + b * v1[i];
+    return true;
+}
+
+}  // namespace
+
+int b200_interpolate_vectors(const double* vecs, const double* weights, int n, int dim, int method, double* out,
+                             int* out_error_kind) {
+    return mb::guarded([&] {
+        MB_CHECK_ARG(out_error_kind != nullptr, "out_error_kind is NULL");
+        *out_error_kind = B200_INTERP_OK;
+        MB_CHECK_ARG(vecs && weights && out, "NULL argument");
+        MB_CHECK_ARG(n > 0 && dim > 0, "Cannot interpolate an empty list of vectors");
+        MB_CHECK_ARG(method >= B200_INTERP_LERP && method <= B200_INTERP_SLERP, "unknown interpolation method %d", method);
+        if (method == B200_INTERP_LERP || method == B200_INTERP_NLERP) {
+            double wsum = 0.0;
+            for (int i = 0; i < n; ++i) wsum += weights[i];
+            if (wsum == 0.0) {
+                *out_error_kind = B200_INTERP_ZERO_SUM_WEIGHTS;
+                mb::fail(B200_ERR_INVALID_ARG,
+                         "Sum of weights is zero. LERP cannot interpolate vectors with zero sum of weights");
+            }
+            for (int d = 0; d < dim; ++d) out[d] = 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double w = weights[i] / wsum;
+                for (int d = 0; d < dim; ++d) out[d] += w * vecs[(size_t)i * dim + d];
+            }
+            if (method == B200_INTERP_NLERP) {
+                double ss = 0.0;
+                for (int d = 0; d < dim; ++d) ss += out[d] * out[d];
+                const double len = sqrt(ss);
+                if (len == 0.0) {
+                    *out_error_kind = B200_INTERP_ZERO_MAGNITUDE;
+                    mb::fail(B200_ERR_INVALID_ARG,
+                             "Interpolated vector has zero magnitude. Cannot normalize a vector with zero magnitude");
+                }
+                for (int d = 0; d < dim; ++d) out[d] /= len;
+            }
+            return;
+        }
+        // SLERP, hierarchical (the only variant from_interpolation_method builds, :39-40,124-125): neighbours are
+        // merged pairwise with t = w1 / (w0 + w1), the merged vector carries weight (w0 + w1) / 2, an odd tail is
+        // carried to the next level unchanged (:212-237).
+        std::vector<double> cur(vecs, vecs + (size_t)n * dim), next;
+        std::vector<double> w(weights, weights + n), nw;
+        int m = n;
+        while (m > 1) {
+            const int half = (m + 1) / 2;
+            next.assign((size_t)half * dim, 0.0);
+            nw.assign(half, 0.0);
+            for (int i = 0; i < m; i += 2) {
+                if (i + 1 == m) {
+                    std::copy(cur.begin() + (size_t)i * dim, cur.begin() + (size_t)(i + 1) * dim,
+                              next.begin() + (size_t)(i / 2) * dim);
+                    nw[i / 2] = w[i];
+                    continue;
+                }
+                const double sum = w[i] + w[i + 1];
+                if (sum == 0.0) {
+                    *out_error_kind = B200_INTERP_ZERO_SUM_WEIGHTS;
+                    mb::fail(B200_ERR_INVALID_ARG,
+                             "Sum of weights %g and %g is zero. SLERP cannot interpolate vectors with a sum weight of zero",
+                             w[i], w[i + 1]);
+                }
+                if (!slerp_pair(&cur[(size_t)i * dim], &cur[(size_t)(i + 1) * dim], w[i + 1] / sum, dim,
+                                &next[(size_t)(i / 2) * dim])) {
+                    *out_error_kind = B200_INTERP_ZERO_LENGTH;
+                    mb::fail(B200_ERR_INVALID_ARG,
+                             "One or more vectors had zero length. SLERP cannot interpolate vectors with zero length");
+                }
+                nw[i / 2] = sum / 2.0;
+            }
+            cur.swap(next);
+            w.swap(nw);
+            m = half;
+        }
+        std::copy(cur.begin(), cur.begin() + dim, out);
     });
 }
 

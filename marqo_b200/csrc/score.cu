@@ -53,14 +53,33 @@ struct ScanParams {
     const float* row_bias;      // used when HAS_BIAS: score = 2 * dot - row_bias[row]  (euclidean: |row|^2)
     const float* bound_score;   // optional [MQ]: only rows strictly after (bound_score, bound_row) qualify
     const int32_t* bound_row;
+    const float2* mod;          // used when HAS_MOD: per-document (mult, add); key = mult * closeness + add
+    const float* q_n2;          // used when HAS_MOD and euclidean: |q|^2 per query
+    int metric;
     float* out_score;           // [grid][MQ][KP]
     int32_t* out_row;
     int32_t* out_doc;
 };
 
-__host__ __device__ inline size_t scan_smem_bytes(int dim, int stages) {
+__host__ __device__ inline size_t scan_smem_bytes(int dim, int stages, bool has_mod = false) {
     return (size_t)(dim / BLOCK_K) * QCHUNK_BYTES + (size_t)stages * STAGE_BYTES + 2 * 4 * TILE_N * sizeof(int32_t) +
-           (2 * 16 + 2 * ACC_STAGES + 2) * sizeof(uint64_t) + 1024 /* alignment slack */;
+           (has_mod ? 4 * TILE_N * sizeof(float2) : 0) + (2 * 16 + 2 * ACC_STAGES + 2) * sizeof(uint64_t) +
+           1024 /* alignment slack */;
+}
+
+// fp32 closeness of the scan key (dot product, or 2 dot - |row|^2 for euclidean); the exact fp64 form is
+// closeness_from_dot() below.  Only evaluated when score modifiers make the ranking non-monotone in the dot product.
+__device__ __forceinline__ float closeness_approx(float v, int metric, float qn2) {
+    switch (metric) {
+        case B200_METRIC_EUCLIDEAN:
+            return __fdividef(1.0f, 1.0f + sqrtf(fmaxf(qn2 - v, 0.0f)));
+        case B200_METRIC_PRENORMALIZED_ANGULAR:
+            return __fdividef(1.0f, 2.0f - v);
+        case B200_METRIC_ANGULAR:
+            return __fdividef(1.0f, 1.0f + acosf(fminf(1.0f, fmaxf(-1.0f, v))));
+        default:
+            return v;
+    }
 }
 
 __device__ __forceinline__ float pick32(const uint32_t (&v)[32], int j) {
@@ -112,7 +131,7 @@ __device__ __forceinline__ void list_insert(float (&ls)[KP], int (&lr)[KP], int 
     }
 }
 
-template <bool HAS_DOCS, bool HAS_BIAS>
+template <bool HAS_DOCS, bool HAS_BIAS, bool HAS_MOD>
 __global__ void __launch_bounds__(THREADS, 1)
 scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_q, ScanParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -123,7 +142,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ 
     uint8_t* smem_c = smem_q + (size_t)kblocks * QCHUNK_BYTES;
     int32_t* smem_docs = reinterpret_cast<int32_t*>(smem_c + (size_t)S * STAGE_BYTES);
     float* smem_bias = reinterpret_cast<float*>(smem_docs + 4 * TILE_N);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_bias + 4 * TILE_N);
+    float2* smem_mod = reinterpret_cast<float2*>(smem_bias + 4 * TILE_N);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_mod + (HAS_MOD ? 4 * TILE_N : 0));
     uint64_t* empty = full + 16;
     uint64_t* tfull = empty + 16;
     uint64_t* tempty = tfull + ACC_STAGES;
@@ -219,6 +239,8 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ 
         const bool active = lane < 16 && q < p.nq;
         int32_t* my_docs = smem_docs + (warp - 2) * TILE_N;
         float* my_bias = smem_bias + (warp - 2) * TILE_N;
+        float2* my_mod = smem_mod + (HAS_MOD ? (warp - 2) * TILE_N : 0);
+        const float my_qn2 = (HAS_MOD && p.q_n2 != nullptr && active) ? p.q_n2[q] : 0.f;
         float ls[KP];
         int lr[KP], ld[KP];
 #pragma unroll
@@ -239,13 +261,18 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ 
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
             const int row0 = tile * TILE_N;
-            if (HAS_DOCS || HAS_BIAS) {
+            if (HAS_DOCS || HAS_BIAS || HAS_MOD) {
                 __syncwarp();
 #pragma unroll
                 for (int t = 0; t < 4; ++t) {
                     int r = row0 + t * 32 + lane;
-                    if (HAS_DOCS) my_docs[t * 32 + lane] = r < p.n_rows ? __ldg(p.doc_of_row + r) : -1;
+                    int d = r;
+                    if (HAS_DOCS) {
+                        d = r < p.n_rows ? __ldg(p.doc_of_row + r) : -1;
+                        my_docs[t * 32 + lane] = d;
+                    }
                     if (HAS_BIAS) my_bias[t * 32 + lane] = r < p.n_rows ? __ldg(p.row_bias + r) : 0.f;
+                    if (HAS_MOD) my_mod[t * 32 + lane] = (r < p.n_rows && d >= 0) ? __ldg(p.mod + d) : make_float2(0.f, 0.f);
                 }
                 __syncwarp();
             }
@@ -262,6 +289,13 @@ scan_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ 
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             v[j] = __float_as_uint(fmaf(2.0f, __uint_as_float(v[j]), -my_bias[c * 32 + j]));
+                    }
+                    if (HAS_MOD) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float2 ma = my_mod[c * 32 + j];
+                            v[j] = __float_as_uint(fmaf(ma.x, closeness_approx(__uint_as_float(v[j]), p.metric, my_qn2), ma.y));
+                        }
                     }
                     uint32_t mask = 0;
 #pragma unroll
@@ -332,6 +366,8 @@ struct MergeParams {
     // optional candidate dump for multi-round search: [nq][KP] sorted by (approx desc, row asc)
     float* cand_score;
     int32_t* cand_row;
+    // optional score modifiers: per-document (mult, add) in fp64; final key = mult * closeness + add
+    const double2* mod64;
 };
 
 __device__ __forceinline__ bool approx_before(float sa, int ra, float sb, int rb) {
@@ -485,12 +521,18 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeParams p) {
         }
         double tot = 0.0;
         for (int l = 0; l < 32; ++l) tot += __shfl_sync(0xffffffffu, part, l);
-        if (lane == 0) sel_dot[c] = tot;
+        if (lane == 0) {
+            if (p.mod64) {   // the ordering key becomes the modified score (separate multiply and add, no fma)
+                const double2 ma = p.mod64[sel_doc[c]];
+                tot = __dadd_rn(__dmul_rn(ma.x, closeness_from_dot(tot, p.metric)), ma.y);
+            }
+            sel_dot[c] = tot;
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         const int n = sel_n;
-        // insertion sort by (dot desc, doc asc)
+        // insertion sort by (key desc, doc asc); key = exact dot product, or the modified score
         for (int i = 1; i < n; ++i) {
             const double d = sel_dot[i];
             const int r = sel_row[i], dc = sel_doc[i];
@@ -510,7 +552,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_kernel(MergeParams p) {
             if (i < n) {
                 p.out_doc[o] = sel_doc[i] + p.doc_offset;
                 p.out_row[o] = sel_row[i];
-                p.out_score[o] = closeness_from_dot(sel_dot[i], p.metric);
+                p.out_score[o] = p.mod64 ? sel_dot[i] : closeness_from_dot(sel_dot[i], p.metric);
             } else {
                 p.out_doc[o] = -1;
                 p.out_row[o] = -1;
@@ -585,6 +627,70 @@ __global__ void next_bound_kernel(const float* cand_score, const int32_t* cand_r
     const int r = cand_row[q * KP + KP - 1];
     bound_score[q] = r >= 0 ? cand_score[q * KP + KP - 1] : -INFINITY;
     bound_row[q] = r >= 0 ? r : INT_MAX;
+}
+
+// Score modifiers (reference: the rank-profile function `modify`, unstructured_vespa_schema.py:266-271):
+//   mult = count(mult_w * attr) == 0 ? 1 : prod(mult_w * attr);   add = sum(add_w * attr)
+// over the attribute cells a document HAS (NaN = missing cell of the sparse tensor<double>(p{})), in the order the
+// caller lists the columns.  Written in fp64 for the exact merge and in fp32 for the scan.
+constexpr int MAX_MOD_TERMS = 16;
+struct ModifierParams {
+    int n_docs;
+    int attr_cap;
+    int n_mult, n_add;
+    const double* mult_col[MAX_MOD_TERMS];
+    const double* add_col[MAX_MOD_TERMS];
+    double mult_w[MAX_MOD_TERMS];
+    double add_w[MAX_MOD_TERMS];
+    double2* out64;
+    float2* out32;
+    int* negative_flag;
+};
+
+__global__ void modifier_kernel(ModifierParams p) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= p.n_docs) return;
+    double m = 1.0, a = 0.0;
+    int cnt = 0;
+    for (int i = 0; i < p.n_mult; ++i) {
+        const double v = (p.mult_col[i] && d < p.attr_cap) ? p.mult_col[i][d] : NAN;
+        if (v == v) {
+            m = __dmul_rn(m, __dmul_rn(p.mult_w[i], v));
+            ++cnt;
+        }
+    }
+    if (cnt == 0) m = 1.0;
+    for (int i = 0; i < p.n_add; ++i) {
+        const double v = (p.add_col[i] && d < p.attr_cap) ? p.add_col[i][d] : NAN;
+        if (v == v) a = __dadd_rn(a, __dmul_rn(p.add_w[i], v));
+    }
+    p.out64[d] = make_double2(m, a);
+    p.out32[d] = make_float2((float)m, (float)a);
+    if (m < 0.0) atomicOr(p.negative_flag, 1);
+}
+
+__global__ void fill_nan_kernel(double* dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = NAN;
+}
+
+__global__ void scatter_attr_kernel(double* col, const int32_t* docs, const double* vals, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) col[docs[i]] = vals ? vals[i] : NAN;
+}
+
+__global__ void query_norms_kernel(const __half* __restrict__ qh, int dim, float* __restrict__ out) {
+    // one warp per query row of the [MQ, dim] fp16 block
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= MQ) return;
+    float n2 = 0.f;
+    for (int i = lane; i < dim; i += 32) {
+        const float f = __half2float(qh[(size_t)q * dim + i]);
+        n2 = fmaf(f, f, n2);
+    }
+    for (int o = 16; o > 0; o >>= 1) n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+    if (lane == 0) out[q] = n2;
 }
 
 // Merge of all-gathered per-shard lists on the device: one warp per query, candidates strided over the lanes,
@@ -701,6 +807,16 @@ struct b200_index {
     double* o_score = nullptr;
     float *cand_score = nullptr, *bound_score = nullptr;   // [MQ, KP] / [MQ]: multi-round search (k > K_SINGLE)
     int32_t *cand_row = nullptr, *bound_row = nullptr;
+    // score modifiers: per-document numeric attributes (one device column per attribute name, NaN = missing)
+    std::vector<double*> attr_cols;
+    int64_t attr_cap = 0;          // documents each column can hold
+    int64_t max_doc = -1;          // largest explicit document number seen by add()
+    double2* mod64 = nullptr;      // [mod_cap] (mult, add) of the current modified search
+    float2* mod32 = nullptr;
+    int64_t mod_cap = 0;
+    float* q_n2 = nullptr;         // [MQ] |q|^2 (euclidean + modifiers)
+    int* d_flag = nullptr;
+    bool mod_active = false;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -728,6 +844,11 @@ void index_free(b200_index* ix) {
     cudaFree(ix->cand_row);
     cudaFree(ix->bound_score);
     cudaFree(ix->bound_row);
+    for (double* c : ix->attr_cols) cudaFree(c);
+    cudaFree(ix->mod64);
+    cudaFree(ix->mod32);
+    cudaFree(ix->q_n2);
+    cudaFree(ix->d_flag);
     for (auto& e : ix->ev)
         if (e) cudaEventDestroy(e);
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
@@ -810,11 +931,18 @@ b200_index* index_new(int device, int dim, int metric, int64_t capacity_rows) {
         cuda_alloc((void**)&ix->cand_row, (size_t)MQ * KP * sizeof(int32_t));
         cuda_alloc((void**)&ix->bound_score, (size_t)MQ * sizeof(float));
         cuda_alloc((void**)&ix->bound_row, (size_t)MQ * sizeof(int32_t));
+        cuda_alloc((void**)&ix->q_n2, (size_t)MQ * sizeof(float));
+        cuda_alloc((void**)&ix->d_flag, sizeof(int));
         ensure_capacity(ix, std::max<int64_t>(capacity_rows, TILE_N));
-        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        const auto smem_attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false, false, false>, smem_attr, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true, false, false>, smem_attr, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false, true, false>, smem_attr, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true, true, false>, smem_attr, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false, false, true>, smem_attr, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true, false, true>, smem_attr, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<false, true, true>, smem_attr, SMEM_LIMIT));
+        MB_CUDA(cudaFuncSetAttribute(scan_kernel<true, true, true>, smem_attr, SMEM_LIMIT));
         MB_CUDA(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     } catch (...) {
         index_free(ix);
@@ -855,9 +983,10 @@ void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_
     }
     const int num_tiles = (int)((ix->n_rows + TILE_N - 1) / TILE_N);
     const int grid = std::min(num_tiles, ix->sms);
+    const bool mod = ix->mod_active;
     int stages = 16;
-    while (stages > 2 && scan_smem_bytes(ix->dim, stages) > (size_t)SMEM_LIMIT) --stages;
-    const size_t smem = scan_smem_bytes(ix->dim, stages);
+    while (stages > 2 && scan_smem_bytes(ix->dim, stages, mod) > (size_t)SMEM_LIMIT) --stages;
+    const size_t smem = scan_smem_bytes(ix->dim, stages, mod);
     if (smem > (size_t)SMEM_LIMIT) fail(B200_ERR_INTERNAL, "scan kernel shared memory budget exceeded");
 
     CUtensorMap tmap_c = make_tmap_2d(ix->corpus, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (uint64_t)ix->dim,
@@ -878,17 +1007,18 @@ void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_
     sp.out_score = ix->list_score;
     sp.out_row = ix->list_row;
     sp.out_doc = ix->list_doc;
+    sp.mod = mod ? ix->mod32 : nullptr;
+    sp.q_n2 = (mod && ix->metric == B200_METRIC_EUCLIDEAN) ? ix->q_n2 : nullptr;
+    sp.metric = ix->metric;
 
     if (record_timing) MB_CUDA(cudaEventRecord(ix->ev[0], ix->stream));
     const bool bias = ix->metric == B200_METRIC_EUCLIDEAN;
-    if (ix->has_docs && bias)
-        scan_kernel<true, true><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
-    else if (ix->has_docs)
-        scan_kernel<true, false><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
-    else if (bias)
-        scan_kernel<false, true><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
-    else
-        scan_kernel<false, false><<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
+    using ScanFn = void (*)(const CUtensorMap, const CUtensorMap, ScanParams);
+    static const ScanFn table[8] = {scan_kernel<false, false, false>, scan_kernel<true, false, false>,
+                                    scan_kernel<false, true, false>,  scan_kernel<true, true, false>,
+                                    scan_kernel<false, false, true>,  scan_kernel<true, false, true>,
+                                    scan_kernel<false, true, true>,   scan_kernel<true, true, true>};
+    table[(ix->has_docs ? 1 : 0) | (bias ? 2 : 0) | (mod ? 4 : 0)]<<<grid, THREADS, smem, ix->stream>>>(tmap_c, tmap_q, sp);
     MB_CUDA(cudaGetLastError());
     if (record_timing) MB_CUDA(cudaEventRecord(ix->ev[1], ix->stream));
 
@@ -912,6 +1042,7 @@ void search_group(b200_index* ix, int nq, int k, int32_t* d_out_doc, int32_t* d_
     mp.out_score = d_out_score;
     mp.cand_score = cand_score;
     mp.cand_row = cand_row;
+    mp.mod64 = mod ? ix->mod64 : nullptr;
     merge_kernel<<<nq, MERGE_THREADS, (size_t)sort_n * 12, ix->stream>>>(mp);
     MB_CUDA(cudaGetLastError());
     if (record_timing) {
@@ -996,6 +1127,10 @@ void search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_o
         convert_rows_kernel<<<MQ / 8, 256, 0, ix->stream>>>(d_q + (size_t)q0 * ix->dim, ix->qh, g, ix->dim, MQ,
                                                             ix->metric == B200_METRIC_ANGULAR);
         MB_CUDA(cudaGetLastError());
+        if (ix->mod_active && ix->metric == B200_METRIC_EUCLIDEAN) {
+            query_norms_kernel<<<MQ / 8, 256, 0, ix->stream>>>(ix->qh, ix->dim, ix->q_n2);
+            MB_CUDA(cudaGetLastError());
+        }
         if (k <= K_SINGLE)
             search_group(ix, g, k, d_out_doc + (size_t)q0 * k, d_out_row + (size_t)q0 * k, d_out_score + (size_t)q0 * k,
                          q0 + MQ >= nq);
@@ -1011,6 +1146,135 @@ void check_search_args(b200_index* ix, const void* q, int nq, int k, const void*
     MB_CHECK_ARG(nq > 0, "nq must be positive (got %d)", nq);
     MB_CHECK_ARG(k > 0, "k must be positive (got %d)", k);
     MB_CHECK_ARG(k <= 10000, "k = %d exceeds 10000 (Marqo's own limit + offset cap, tensor_search.py:1568-1588)", k);
+}
+
+// largest document number among device-resident ids (ingest path; sizes the score-modifier tables)
+void track_max_doc(b200_index* ix, const int32_t* d_ids, int64_t m) {
+    std::vector<int32_t> h((size_t)m);
+    MB_CUDA(cudaMemcpy(h.data(), d_ids, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    for (int32_t v : h) ix->max_doc = std::max<int64_t>(ix->max_doc, v);
+}
+
+int64_t num_docs(const b200_index* ix) { return std::max<int64_t>(ix->n_rows, ix->max_doc + 1); }
+
+void fill_nan(b200_index* ix, double* dst, int64_t n) {
+    if (n <= 0) return;
+    fill_nan_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(dst, n);
+    MB_CUDA(cudaGetLastError());
+}
+
+void ensure_attr_capacity(b200_index* ix, int64_t need_docs) {
+    if (need_docs <= ix->attr_cap) return;
+    const int64_t cap = (int64_t)round_up((size_t)std::max<int64_t>(need_docs, ix->attr_cap + ix->attr_cap / 2), 1024);
+    for (double*& col : ix->attr_cols) {
+        if (!col) continue;
+        double* nc = nullptr;
+        cuda_alloc((void**)&nc, (size_t)cap * sizeof(double));
+        if (ix->attr_cap > 0)
+            MB_CUDA(cudaMemcpyAsync(nc, col, (size_t)ix->attr_cap * sizeof(double), cudaMemcpyDeviceToDevice, ix->stream));
+        fill_nan(ix, nc + ix->attr_cap, cap - ix->attr_cap);
+        MB_CUDA(cudaStreamSynchronize(ix->stream));
+        cudaFree(col);
+        col = nc;
+    }
+    ix->attr_cap = cap;
+}
+
+double* attr_column(b200_index* ix, int column) {
+    if ((int)ix->attr_cols.size() <= column) ix->attr_cols.resize(column + 1, nullptr);
+    if (!ix->attr_cols[column]) {
+        cuda_alloc((void**)&ix->attr_cols[column], (size_t)ix->attr_cap * sizeof(double));
+        fill_nan(ix, ix->attr_cols[column], ix->attr_cap);
+    }
+    return ix->attr_cols[column];
+}
+
+struct ModScope {  // marks the index as "searching with modifiers" for the duration of one call
+    b200_index* ix;
+    explicit ModScope(b200_index* i) : ix(i) { ix->mod_active = true; }
+    ~ModScope() { ix->mod_active = false; }
+};
+
+void prepare_modifiers(b200_index* ix, const int32_t* mult_cols, const double* mult_w, int n_mult,
+                       const int32_t* add_cols, const double* add_w, int n_add) {
+    const int64_t nd = num_docs(ix);
+    if (nd > ix->mod_cap) {
+        cudaFree(ix->mod64);
+        cudaFree(ix->mod32);
+        ix->mod64 = nullptr;
+        ix->mod32 = nullptr;
+        ix->mod_cap = 0;
+        const int64_t cap = (int64_t)round_up((size_t)nd + (size_t)nd / 2, 1024);
+        cuda_alloc((void**)&ix->mod64, (size_t)cap * sizeof(double2));
+        cuda_alloc((void**)&ix->mod32, (size_t)cap * sizeof(float2));
+        ix->mod_cap = cap;
+    }
+    if (nd == 0) return;
+    ModifierParams mp{};
+    mp.n_docs = (int)nd;
+    mp.attr_cap = (int)ix->attr_cap;
+    mp.n_mult = n_mult;
+    mp.n_add = n_add;
+    auto col = [&](int c) -> const double* {
+        MB_CHECK_ARG(c >= 0 && c < B200_MAX_ATTRIBUTE_COLUMNS, "attribute column %d out of range", c);
+        return c < (int)ix->attr_cols.size() ? ix->attr_cols[c] : nullptr;   // never-set column: missing everywhere
+    };
+    for (int i = 0; i < n_mult; ++i) {
+        mp.mult_col[i] = col(mult_cols[i]);
+        mp.mult_w[i] = mult_w[i];
+    }
+    for (int i = 0; i < n_add; ++i) {
+        mp.add_col[i] = col(add_cols[i]);
+        mp.add_w[i] = add_w[i];
+    }
+    mp.out64 = ix->mod64;
+    mp.out32 = ix->mod32;
+    mp.negative_flag = ix->d_flag;
+    MB_CUDA(cudaMemsetAsync(ix->d_flag, 0, sizeof(int), ix->stream));
+    modifier_kernel<<<(unsigned)((nd + 255) / 256), 256, 0, ix->stream>>>(mp);
+    MB_CUDA(cudaGetLastError());
+    int flag = 0;
+    MB_CUDA(cudaMemcpyAsync(&flag, ix->d_flag, sizeof(int), cudaMemcpyDeviceToHost, ix->stream));
+    MB_CUDA(cudaStreamSynchronize(ix->stream));
+    // closeness(field, embeddings) is the best chunk's closeness; the scan keeps, per document, the chunk with the best
+    // MODIFIED key, which is the same chunk only while the multiplier is >= 0.
+    if (flag && ix->has_docs)
+        fail(B200_ERR_UNSUPPORTED,
+             "a negative multiplicative score modifier on a corpus with explicit document ids (multi-chunk documents) "
+             "is not supported");
+}
+
+void search_host(b200_index* ix, const float* q, int nq, int k, int32_t* out_doc, int32_t* out_row, double* out_score) {
+    int32_t *dd = ix->o_doc, *dr = ix->o_row;
+    double* ds = ix->o_score;
+    void* tmp[3] = {nullptr, nullptr, nullptr};
+    if (k > KP) {  // the resident [MQ, KP] output block is too small for a large k
+        cuda_alloc(&tmp[0], (size_t)MQ * k * sizeof(int32_t));
+        cuda_alloc(&tmp[1], (size_t)MQ * k * sizeof(int32_t));
+        cuda_alloc(&tmp[2], (size_t)MQ * k * sizeof(double));
+        dd = (int32_t*)tmp[0];
+        dr = (int32_t*)tmp[1];
+        ds = (double*)tmp[2];
+    }
+    try {
+        for (int q0 = 0; q0 < nq; q0 += MQ) {
+            const int gq = std::min(MQ, nq - q0);
+            MB_CUDA(cudaMemcpyAsync(ix->q_stage, q + (size_t)q0 * ix->dim, (size_t)gq * ix->dim * sizeof(float),
+                                    cudaMemcpyHostToDevice, ix->stream));
+            search_device(ix, ix->q_stage, gq, k, dd, dr, ds);
+            MB_CUDA(cudaMemcpyAsync(out_doc + (size_t)q0 * k, dd, (size_t)gq * k * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, ix->stream));
+            MB_CUDA(cudaMemcpyAsync(out_row + (size_t)q0 * k, dr, (size_t)gq * k * sizeof(int32_t),
+                                    cudaMemcpyDeviceToHost, ix->stream));
+            MB_CUDA(cudaMemcpyAsync(out_score + (size_t)q0 * k, ds, (size_t)gq * k * sizeof(double),
+                                    cudaMemcpyDeviceToHost, ix->stream));
+            MB_CUDA(cudaStreamSynchronize(ix->stream));
+        }
+    } catch (...) {
+        for (void* t : tmp) cudaFree(t);
+        throw;
+    }
+    for (void* t : tmp) cudaFree(t);
 }
 
 }  // namespace
@@ -1039,7 +1303,10 @@ int b200_index_add(b200_index* ix, const float* vecs, const int32_t* doc_ids, in
         DeviceGuard g(ix->device);
         MB_CHECK_ARG(ix->n_rows + m < (int64_t)INT32_MAX, "row count would exceed 2^31-1");
         if (doc_ids)
-            for (int64_t i = 0; i < m; ++i) MB_CHECK_ARG(doc_ids[i] >= 0, "doc_ids[%lld] is negative", (long long)i);
+            for (int64_t i = 0; i < m; ++i) {
+                MB_CHECK_ARG(doc_ids[i] >= 0, "doc_ids[%lld] is negative", (long long)i);
+                ix->max_doc = std::max<int64_t>(ix->max_doc, doc_ids[i]);
+            }
         // When explicit ids are given but the index has been identity-mapped so far, the ids must be honoured.
         float* d_v = nullptr;
         int32_t* d_d = nullptr;
@@ -1078,6 +1345,7 @@ int b200_index_add_device(b200_index* ix, const float* d_vecs, const int32_t* d_
         MB_CHECK_ARG(ix->n_rows + m < (int64_t)INT32_MAX, "row count would exceed 2^31-1");
         add_rows_device(ix, d_vecs, d_doc_ids, m);
         MB_CUDA(cudaStreamSynchronize(ix->stream));
+        if (d_doc_ids) track_max_doc(ix, d_doc_ids, m);
     });
 }
 
@@ -1132,36 +1400,72 @@ int b200_index_search(b200_index* ix, const float* q, int nq, int k, int32_t* ou
         check_search_args(ix, q, nq, k, out_doc, out_row, out_score);
         std::lock_guard<std::mutex> lk(ix->mu);
         DeviceGuard g(ix->device);
-        int32_t *dd = ix->o_doc, *dr = ix->o_row;
-        double* ds = ix->o_score;
-        void* tmp[3] = {nullptr, nullptr, nullptr};
-        if (k > KP) {  // the resident [MQ, KP] output block is too small for a large k
-            cuda_alloc(&tmp[0], (size_t)MQ * k * sizeof(int32_t));
-            cuda_alloc(&tmp[1], (size_t)MQ * k * sizeof(int32_t));
-            cuda_alloc(&tmp[2], (size_t)MQ * k * sizeof(double));
-            dd = (int32_t*)tmp[0];
-            dr = (int32_t*)tmp[1];
-            ds = (double*)tmp[2];
+        search_host(ix, q, nq, k, out_doc, out_row, out_score);
+    });
+}
+
+int b200_index_search_modified(b200_index* ix, const float* q, int nq, int k, const int32_t* mult_cols,
+                               const double* mult_w, int n_mult, const int32_t* add_cols, const double* add_w, int n_add,
+                               int32_t* out_doc, int32_t* out_row, double* out_score) {
+    return guarded([&] {
+        check_search_args(ix, q, nq, k, out_doc, out_row, out_score);
+        MB_CHECK_ARG(n_mult >= 0 && n_mult <= MAX_MOD_TERMS && n_add >= 0 && n_add <= MAX_MOD_TERMS,
+                     "at most %d multiplicative and %d additive modifiers per search", MAX_MOD_TERMS, MAX_MOD_TERMS);
+        MB_CHECK_ARG((n_mult == 0 || (mult_cols && mult_w)) && (n_add == 0 || (add_cols && add_w)), "NULL modifier list");
+        for (int i = 0; i < n_mult; ++i) MB_CHECK_ARG(std::isfinite(mult_w[i]), "mult_w[%d] is not finite", i);
+        for (int i = 0; i < n_add; ++i) MB_CHECK_ARG(std::isfinite(add_w[i]), "add_w[%d] is not finite", i);
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        prepare_modifiers(ix, mult_cols, mult_w, n_mult, add_cols, add_w, n_add);
+        ModScope scope(ix);
+        search_host(ix, q, nq, k, out_doc, out_row, out_score);
+    });
+}
+
+int b200_index_set_attributes(b200_index* ix, int column, const int32_t* doc_ids, const double* values, int64_t n) {
+    return guarded([&] {
+        MB_CHECK_ARG(ix != nullptr, "index is NULL");
+        MB_CHECK_ARG(n >= 0, "n must be >= 0");
+        MB_CHECK_ARG(column >= -1 && column < B200_MAX_ATTRIBUTE_COLUMNS, "attribute column %d out of range", column);
+        MB_CHECK_ARG(column >= 0 || values == nullptr, "column -1 (all columns) only clears: values must be NULL");
+        if (n == 0) return;
+        MB_CHECK_ARG(doc_ids != nullptr, "doc_ids is NULL");
+        int64_t hi = -1;
+        for (int64_t i = 0; i < n; ++i) {
+            MB_CHECK_ARG(doc_ids[i] >= 0, "doc_ids[%lld] is negative", (long long)i);
+            hi = std::max<int64_t>(hi, doc_ids[i]);
+            if (values) MB_CHECK_ARG(std::isfinite(values[i]), "values[%lld] is not finite", (long long)i);
         }
+        std::lock_guard<std::mutex> lk(ix->mu);
+        DeviceGuard g(ix->device);
+        ensure_attr_capacity(ix, hi + 1);
+        int32_t* d_ids = nullptr;
+        double* d_vals = nullptr;
+        cuda_alloc((void**)&d_ids, (size_t)n * sizeof(int32_t));
         try {
-            for (int q0 = 0; q0 < nq; q0 += MQ) {
-                const int gq = std::min(MQ, nq - q0);
-                MB_CUDA(cudaMemcpyAsync(ix->q_stage, q + (size_t)q0 * ix->dim, (size_t)gq * ix->dim * sizeof(float),
-                                        cudaMemcpyHostToDevice, ix->stream));
-                search_device(ix, ix->q_stage, gq, k, dd, dr, ds);
-                MB_CUDA(cudaMemcpyAsync(out_doc + (size_t)q0 * k, dd, (size_t)gq * k * sizeof(int32_t),
-                                        cudaMemcpyDeviceToHost, ix->stream));
-                MB_CUDA(cudaMemcpyAsync(out_row + (size_t)q0 * k, dr, (size_t)gq * k * sizeof(int32_t),
-                                        cudaMemcpyDeviceToHost, ix->stream));
-                MB_CUDA(cudaMemcpyAsync(out_score + (size_t)q0 * k, ds, (size_t)gq * k * sizeof(double),
-                                        cudaMemcpyDeviceToHost, ix->stream));
-                MB_CUDA(cudaStreamSynchronize(ix->stream));
+            if (values) cuda_alloc((void**)&d_vals, (size_t)n * sizeof(double));
+            MB_CUDA(cudaMemcpyAsync(d_ids, doc_ids, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, ix->stream));
+            if (values)
+                MB_CUDA(cudaMemcpyAsync(d_vals, values, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ix->stream));
+            const unsigned blocks = (unsigned)((n + 255) / 256);
+            if (column >= 0) {
+                scatter_attr_kernel<<<blocks, 256, 0, ix->stream>>>(attr_column(ix, column), d_ids, d_vals, n);
+                MB_CUDA(cudaGetLastError());
+            } else {
+                for (double* col : ix->attr_cols)
+                    if (col) {
+                        scatter_attr_kernel<<<blocks, 256, 0, ix->stream>>>(col, d_ids, nullptr, n);
+                        MB_CUDA(cudaGetLastError());
+                    }
             }
+            MB_CUDA(cudaStreamSynchronize(ix->stream));
         } catch (...) {
-            for (void* t : tmp) cudaFree(t);
+            cudaFree(d_ids);
+            cudaFree(d_vals);
             throw;
         }
-        for (void* t : tmp) cudaFree(t);
+        cudaFree(d_ids);
+        cudaFree(d_vals);
     });
 }
 
@@ -1270,7 +1574,7 @@ int b200_index_save(b200_index* ix, const char* path) {
             int64_t n_rows;
         } hdr;
         memcpy(hdr.magic, "B200IDX\0", 8);
-        hdr.version = 1;
+        hdr.version = 2;   // 2 = version 1 + the attribute-column trailer
         hdr.dim = ix->dim;
         hdr.metric = ix->metric;
         hdr.has_docs = ix->has_docs ? 1 : 0;
@@ -1287,6 +1591,14 @@ int b200_index_save(b200_index* ix, const char* path) {
         MB_CUDA(cudaStreamSynchronize(ix->stream));
         dump(ix->corpus, (size_t)ix->n_rows * ix->dim * sizeof(__half));
         dump(ix->doc_of_row, (size_t)ix->n_rows * sizeof(int32_t));
+        // trailer: score-modifier attribute columns
+        const int64_t trailer[3] = {ix->max_doc, ix->attr_cap, (int64_t)ix->attr_cols.size()};
+        ok = ok && fwrite(trailer, sizeof(trailer), 1, f) == 1;
+        for (double* col : ix->attr_cols) {
+            const int32_t present = col ? 1 : 0;
+            ok = ok && fwrite(&present, sizeof(present), 1, f) == 1;
+            if (col) dump(col, (size_t)ix->attr_cap * sizeof(double));
+        }
         ok = (fclose(f) == 0) && ok;
         if (!ok) fail(B200_ERR_INTERNAL, "short write to %s", path);
     });
@@ -1305,7 +1617,8 @@ int b200_index_load(int device, const char* path, b200_index** out) {
         } hdr;
         b200_index* ix = nullptr;
         try {
-            if (fread(&hdr, sizeof(hdr), 1, f) != 1 || memcmp(hdr.magic, "B200IDX\0", 8) != 0 || hdr.version != 1)
+            if (fread(&hdr, sizeof(hdr), 1, f) != 1 || memcmp(hdr.magic, "B200IDX\0", 8) != 0 ||
+                (hdr.version != 1 && hdr.version != 2))
                 fail(B200_ERR_INVALID_ARG, "%s is not a marqo_b200 index snapshot", path);
             ix = index_new(device, hdr.dim, hdr.metric, hdr.n_rows);
             DeviceGuard g(device);
@@ -1321,6 +1634,24 @@ int b200_index_load(int device, const char* path, b200_index** out) {
             slurp(ix->doc_of_row, (size_t)hdr.n_rows * sizeof(int32_t));
             ix->n_rows = hdr.n_rows;
             ix->has_docs = hdr.has_docs != 0;
+            if (hdr.version >= 2) {
+                int64_t trailer[3];
+                if (fread(trailer, sizeof(trailer), 1, f) != 1) fail(B200_ERR_INVALID_ARG, "%s is truncated", path);
+                MB_CHECK_ARG(trailer[2] >= 0 && trailer[2] <= B200_MAX_ATTRIBUTE_COLUMNS && trailer[1] >= 0,
+                             "%s has a corrupt attribute trailer", path);
+                ix->max_doc = trailer[0];
+                ix->attr_cap = trailer[1];
+                ix->attr_cols.assign((size_t)trailer[2], nullptr);
+                for (size_t c = 0; c < ix->attr_cols.size(); ++c) {
+                    int32_t present = 0;
+                    if (fread(&present, sizeof(present), 1, f) != 1) fail(B200_ERR_INVALID_ARG, "%s is truncated", path);
+                    if (!present) continue;
+                    cuda_alloc((void**)&ix->attr_cols[c], (size_t)ix->attr_cap * sizeof(double));
+                    slurp(ix->attr_cols[c], (size_t)ix->attr_cap * sizeof(double));
+                }
+            } else if (ix->has_docs && hdr.n_rows > 0) {
+                track_max_doc(ix, ix->doc_of_row, hdr.n_rows);
+            }
             if (ix->metric == B200_METRIC_EUCLIDEAN && hdr.n_rows > 0) {
                 row_norms_kernel<<<(unsigned)((hdr.n_rows + 7) / 8), 256, 0, ix->stream>>>(ix->corpus, hdr.n_rows, hdr.dim,
                                                                                          ix->row_n2);

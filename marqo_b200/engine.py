@@ -104,6 +104,40 @@ class RowStore:
         N.check(self._lib.b200_index_search(self._handle(), _ptr(q), nq, int(k), _ptr(doc), _ptr(row), _ptr(score)))
         return doc, row, score
 
+    # -- score modifiers -----------------------------------------------------------------------
+    def set_attributes(self, column: int, doc_ids: Sequence[int], values: Optional[Sequence[float]]) -> None:
+        """Set (values given) or remove (values None) the numeric attribute `column` of the listed documents;
+        column == -1 with values None removes every attribute of those documents."""
+        d = _as(doc_ids, np.int32)
+        v = None
+        if values is not None:
+            v = _as(values, np.float64)
+            if v.shape != d.shape:
+                raise ValueError("values must have one entry per document")
+        N.check(self._lib.b200_index_set_attributes(self._handle(), int(column), _ptr(d), _ptr(v), d.shape[0]))
+
+    def search_modified(self, queries, k: int, mult: Sequence[Tuple[int, float]] = (),
+                        add: Sequence[Tuple[int, float]] = ()) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """search() ranked by modify(closeness) = prod(w * attr) * closeness + sum(w * attr)
+        (unstructured_vespa_schema.py:266-271).  mult / add: [(attribute column, weight), ...].
+        -> (doc, row, modified score)."""
+        q = _as(queries, np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.ndim != 2 or q.shape[1] != self.dim:
+            raise ValueError(f"expected [nq, {self.dim}] queries, got {q.shape}")
+        nq = q.shape[0]
+        mc = _as([c for c, _ in mult], np.int32)
+        mw = _as([w for _, w in mult], np.float64)
+        ac = _as([c for c, _ in add], np.int32)
+        aw = _as([w for _, w in add], np.float64)
+        doc = np.empty((nq, k), dtype=np.int32)
+        row = np.empty((nq, k), dtype=np.int32)
+        score = np.empty((nq, k), dtype=np.float64)
+        N.check(self._lib.b200_index_search_modified(self._handle(), _ptr(q), nq, int(k), _ptr(mc), _ptr(mw), len(mc),
+                                                     _ptr(ac), _ptr(aw), len(ac), _ptr(doc), _ptr(row), _ptr(score)))
+        return doc, row, score
+
     def search_device(self, d_q_ptr: int, nq: int, k: int, d_doc_ptr: int, d_row_ptr: int, d_score_ptr: int,
                       sync: bool = True) -> None:
         N.check(self._lib.b200_index_search_device(self._handle(), C.c_void_p(d_q_ptr), int(nq), int(k),

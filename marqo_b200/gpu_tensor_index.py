@@ -5,14 +5,17 @@ Drop-in for `Config.vespa_client` (src/marqo/config.py:35) on the dense path: `f
 :267-296, :405-440, :468-500 and src/marqo/vespa/models/{query_result,feed_response,get_document_response,
 delete_document_response}.py.  Tensor queries (ranking == 'embedding_similarity', YQL made only of
 `nearestNeighbor(...)` terms) are answered from the GPU-resident fp16 matrix by the exact score + top-k kernels;
-everything else (bm25, hybrid, filters, score modifiers) is handed to the optional `delegate` — a real VespaClient —
-or rejected with VespaError ("delegate ... rather than answer").
+everything else (bm25, hybrid, filters) is handed to the optional `delegate` — a real VespaClient — or rejected with
+VespaError ("delegate ... rather than answer").
 
 Semantics implemented (from the schema generators the reference ships, executed inside Vespa today):
   score(doc) = max over searched tensor fields, max over chunks, of closeness(q, chunk)
                (unstructured_vespa_schema.py:225-230,292-294; structured_vespa_index.py:645-688)
   matchfeatures: closest(<embeddings field>) = arg-max chunk label, distance(field,<embeddings field>)
                (consumed by _extract_highlights, structured_vespa_index.py:942-1000)
+  score modifiers: relevance = modify(score, query(marqo__mult_weights_tensor), query(marqo__add_weights_tensor))
+               over the document's `marqo__score_modifiers` cells (unstructured_vespa_schema.py:225-230,266-271;
+               vespa_index.py:106-150; unstructured_document.py:110-125), evaluated inside the scan kernel (f3)
 """
 from __future__ import annotations
 
@@ -23,10 +26,17 @@ from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 
+from ._native import ERR_UNSUPPORTED, NativeError
 from .engine import RowStore
 from .errors import VespaError, VespaStatusError
 
 RANK_PROFILE_EMBEDDING_SIMILARITY = "embedding_similarity"   # */common.py
+RANK_PROFILE_EMBEDDING_SIMILARITY_MODIFIERS_2_9 = "embedding_similarity_modifiers"   # */common.py (index version < 2.10)
+SCORE_MODIFIERS_FIELD = "marqo__score_modifiers"             # */common.py SCORE_MODIFIERS
+MULT_WEIGHTS_INPUTS = ("marqo__mult_weights_tensor", "marqo__mult_weights")   # core/constants.py:22-27
+ADD_WEIGHTS_INPUTS = ("marqo__add_weights_tensor", "marqo__add_weights")
+MAX_ATTRIBUTE_COLUMNS = 64
+MAX_MODIFIER_TERMS = 16
 QUERY_INPUT_EMBEDDINGS = ("marqo__query_embedding", "embedding_query")
 EMBEDDINGS_PREFIX = "marqo__embeddings"
 CHUNKS_PREFIX = "marqo__chunks"
@@ -97,6 +107,8 @@ class _Schema:
         self.doc_ids: List[Optional[str]] = []         # document number -> external id (None = deleted)
         self.fields: List[Optional[dict]] = []         # document number -> stored non-vector fields
         self.doc_rows: List[Dict[str, List[int]]] = [] # document number -> field -> rows
+        self.attr_col: Dict[str, int] = {}             # score-modifier attribute name -> device column
+        self.attrs: List[Dict[str, float]] = []        # document number -> its marqo__score_modifiers cells
 
 
 class GpuTensorIndex:
@@ -128,6 +140,22 @@ class GpuTensorIndex:
             if rows:
                 s.stores[f].delete_doc(num)
         s.doc_rows[num] = {}
+        if s.attrs[num]:
+            for store in s.stores.values():
+                store.set_attributes(-1, [num], None)
+            s.attrs[num] = {}
+
+    @staticmethod
+    def _replay_attributes(s: _Schema, store: RowStore) -> None:
+        """A row store created after documents were fed (a new tensor field) gets their attribute cells."""
+        by_col: Dict[int, Tuple[List[int], List[float]]] = {}
+        for num, attrs in enumerate(s.attrs):
+            for name, v in attrs.items():
+                ids, vals = by_col.setdefault(s.attr_col[name], ([], []))
+                ids.append(num)
+                vals.append(v)
+        for col, (ids, vals) in by_col.items():
+            store.set_attributes(col, ids, vals)
 
     def feed_batch(self, batch: List[Any], schema: str, concurrency: Optional[int] = None, timeout: int = 60):
         """vespa_client.py:267-296.  Embeddings arrive as fields['marqo__embeddings[_<field>]'] = {"0": [...], ...}
@@ -151,6 +179,19 @@ class GpuTensorIndex:
                         if mat.size and mat.ndim != 2:
                             raise ValueError(f"field {f}: ragged embeddings")
                         staged[f] = (keys, mat)
+                    cells = fields.get(SCORE_MODIFIERS_FIELD) or {}
+                    if isinstance(cells, dict) and "cells" in cells and isinstance(cells["cells"], (dict, list)):
+                        cells = cells["cells"]          # Vespa's verbose tensor JSON form
+                    if isinstance(cells, list):
+                        cells = {c["address"]["p"]: c["value"] for c in cells}
+                    attrs = {str(name): float(v) for name, v in cells.items()}
+                    for name, v in attrs.items():
+                        if not math.isfinite(v):
+                            raise ValueError(f"score modifier field {name}: value {v} is not finite")
+                        if name not in s.attr_col:
+                            if len(s.attr_col) >= MAX_ATTRIBUTE_COLUMNS:
+                                raise ValueError(f"more than {MAX_ATTRIBUTE_COLUMNS} distinct score-modifier fields")
+                            s.attr_col[name] = len(s.attr_col)
                     num = s.doc_num.get(doc_id)
                     if num is None:
                         num = len(s.doc_ids)
@@ -158,6 +199,7 @@ class GpuTensorIndex:
                         s.doc_ids.append(doc_id)
                         s.fields.append(None)
                         s.doc_rows.append({})
+                        s.attrs.append({})
                     else:
                         self._tombstone(s, num)          # add_documents replaces by _id
                         s.doc_ids[num] = doc_id
@@ -169,6 +211,7 @@ class GpuTensorIndex:
                             store = RowStore(mat.shape[1], metric=self.metric, device=self.device)
                             s.stores[f] = store
                             s.row_chunk[f] = []
+                            self._replay_attributes(s, store)
                         if mat.shape[1] != store.dim:
                             raise ValueError(f"field {f}: embedding dimension {mat.shape[1]} != index dimension {store.dim}")
                         row0 = len(store)
@@ -176,6 +219,10 @@ class GpuTensorIndex:
                         s.row_chunk[f].extend((num, k) for k in keys)
                         s.doc_rows[num][f] = list(range(row0, row0 + len(keys)))
                     s.fields[num] = {k: v for k, v in fields.items() if not k.startswith(EMBEDDINGS_PREFIX)}
+                    s.attrs[num] = attrs
+                    for store in s.stores.values():
+                        for name, v in attrs.items():
+                            store.set_attributes(s.attr_col[name], [num], [v])
                     responses.append({"status": 200, "pathId": path_id, "id": full_id, "message": None})
                 except (ValueError, KeyError, TypeError) as e:
                     errors = True
@@ -184,7 +231,7 @@ class GpuTensorIndex:
 
     # ------------------------------------------------------------------------------------------------ query
     def _is_tensor_query(self, yql: str, ranking: Optional[str], query_features: Optional[dict]) -> bool:
-        if ranking != RANK_PROFILE_EMBEDDING_SIMILARITY:
+        if ranking not in (RANK_PROFILE_EMBEDDING_SIMILARITY, RANK_PROFILE_EMBEDDING_SIMILARITY_MODIFIERS_2_9):
             return False
         m = _WHERE.search(yql or "")
         if not m:
@@ -194,9 +241,15 @@ class GpuTensorIndex:
         if rest:           # an `AND <filter>` suffix (unstructured_vespa_index.py:62-66) or anything else
             return False
         qf = query_features or {}
-        return any(k in qf for k in QUERY_INPUT_EMBEDDINGS) and not any(k.startswith("marqo__mult_weights")
-                                                                          or k.startswith("marqo__add_weights")
-                                                                          for k in qf)
+        if not any(k in qf for k in QUERY_INPUT_EMBEDDINGS):
+            return False
+        for k, v in qf.items():   # lexical / global modifier tensors belong to other rank profiles
+            if (k.startswith("marqo__mult_weights") or k.startswith("marqo__add_weights")) and \
+                    k not in MULT_WEIGHTS_INPUTS + ADD_WEIGHTS_INPUTS and v:
+                return False
+        n_mult = sum(len(qf.get(k) or {}) for k in MULT_WEIGHTS_INPUTS)
+        n_add = sum(len(qf.get(k) or {}) for k in ADD_WEIGHTS_INPUTS)
+        return n_mult <= MAX_MODIFIER_TERMS and n_add <= MAX_MODIFIER_TERMS
 
     def query(self, yql: str, hits: int = 10, ranking: str = None, model_restrict: str = None,
               query_features: Dict[str, Any] = None, timeout: float = None, **kwargs):
@@ -216,22 +269,69 @@ class GpuTensorIndex:
         fields = [t[1] for t in terms]
         qname = next(k for k in QUERY_INPUT_EMBEDDINGS if k in query_features)
         q = np.asarray(query_features[qname], dtype=np.float32)
+        mult: Dict[str, float] = {}
+        add: Dict[str, float] = {}
+        for k in MULT_WEIGHTS_INPUTS:
+            mult.update(self._weights(query_features.get(k)))
+        for k in ADD_WEIGHTS_INPUTS:
+            add.update(self._weights(query_features.get(k)))
         with self._lock:
             s = self._schemas.get(schema)
             children, n_docs = [], 0
             if s is not None:
                 n_docs = sum(1 for d in s.doc_ids if d is not None)
-                children = self._search(s, schema, fields, q, hits, offset)
+                try:
+                    children = self._search(s, schema, fields, q, hits, offset, mult, add)
+                except NativeError as e:
+                    if e.code != ERR_UNSUPPORTED:
+                        raise
+                    if self.delegate is not None:
+                        return self.delegate.query(yql, hits=hits, ranking=ranking, model_restrict=model_restrict,
+                                                   query_features=query_features, timeout=timeout, **kwargs)
+                    raise VespaError(f"GpuTensorIndex cannot answer this query: {e.message}") from e
         js = {"root": {"id": "toplevel", "relevance": 1.0, "fields": {"totalCount": len(children) + offset},
                        "coverage": {"coverage": 100, "documents": n_docs, "full": True, "nodes": 1, "results": 1,
                                     "resultsFull": 1},
                        "children": children}}
         return _wrap_query_result(js)
 
-    def _search(self, s: _Schema, schema: str, fields: List[str], q: np.ndarray, hits: int, offset: int) -> List[dict]:
+    @staticmethod
+    def _weights(tensor) -> Dict[str, float]:
+        """A query tensor<double>(p{}) as Marqo sends it ({field: weight}) or in Vespa's {"cells": ...} forms."""
+        if not tensor:
+            return {}
+        if isinstance(tensor, dict) and "cells" in tensor:
+            tensor = tensor["cells"]
+        if isinstance(tensor, list):
+            return {c["address"]["p"]: float(c["value"]) for c in tensor}
+        return {str(k): float(v) for k, v in tensor.items()}
+
+    @staticmethod
+    def _modifier_of(attrs: Dict[str, float], mult: Dict[str, float], add: Dict[str, float]) -> Tuple[float, float]:
+        """(multiplier, addend) of one document — the host copy of the device table, used to recover the raw
+        closeness for the distance() match-feature."""
+        m, cnt = 1.0, 0
+        for name, w in mult.items():
+            if name in attrs:
+                m *= w * attrs[name]
+                cnt += 1
+        if cnt == 0:
+            m = 1.0
+        a = 0.0
+        for name, w in add.items():
+            if name in attrs:
+                a += w * attrs[name]
+        return m, a
+
+    def _search(self, s: _Schema, schema: str, fields: List[str], q: np.ndarray, hits: int, offset: int,
+                mult: Optional[Dict[str, float]] = None, add: Optional[Dict[str, float]] = None) -> List[dict]:
         k = hits + offset
         if k <= 0:
             return []
+        # a weight on an attribute no document has multiplies / adds nothing anywhere: drop the term
+        mult_cols = [(s.attr_col[n], w) for n, w in (mult or {}).items() if n in s.attr_col]
+        add_cols = [(s.attr_col[n], w) for n, w in (add or {}).items() if n in s.attr_col]
+        modified = bool(mult_cols) or bool(add_cols)
         best: Dict[int, Tuple[float, str, int]] = {}   # doc number -> (score, field, row)
         for f in fields:
             store = s.stores.get(f)
@@ -240,7 +340,10 @@ class GpuTensorIndex:
             if q.shape[-1] != store.dim:
                 raise VespaStatusError(400, f"Expected a tensor of dimension {store.dim} for query input but got "
                                             f"{q.shape[-1]}")
-            doc, row, score = store.search(q[None, :], k)
+            if modified:
+                doc, row, score = store.search_modified(q[None, :], k, mult_cols, add_cols)
+            else:
+                doc, row, score = store.search(q[None, :], k)
             for d, r, sc in zip(doc[0], row[0], score[0]):
                 if d < 0:
                     continue
@@ -252,9 +355,13 @@ class GpuTensorIndex:
         for num, (sc, f, r) in ranked:
             chunk_key = s.row_chunk[f][r][1]
             out_fields = dict(s.fields[num] or {})
+            raw = sc
+            if modified:   # relevance is the modified score; distance() stays the raw one
+                m, a = self._modifier_of(s.attrs[num], mult or {}, add or {})
+                raw = (sc - a) / m if m != 0 else float("nan")
             out_fields[MATCH_FEATURES] = {
                 f"closest({f})": {"type": "tensor<float>(p{})", "cells": {chunk_key: 1.0}},
-                f"distance(field,{f})": self._distance_from_closeness(sc),
+                f"distance(field,{f})": self._distance_from_closeness(raw),
             }
             children.append({"id": f"id:{schema}:{schema}::{s.doc_ids[num]}", "relevance": sc, "source": "content_default",
                              "fields": out_fields})

@@ -164,8 +164,8 @@ static int hit_before(const hit_t* a, const hit_t* b) {
 /* Exact search.  qh [nq, dim] fp16, corpus [n, dim] fp16, doc_of_row [n] (NULL = identity; < 0 = deleted row).
  * Outputs [nq, k]: doc, arg-max row, closeness; unused slots -1 / -1 / -inf.
  * Per document: best row = max dot, ties -> lowest row.  Across documents: (dot desc, doc asc). */
-int oracle_search(const uint16_t* qh, int nq, const uint16_t* corpus, int64_t n, int dim, const int32_t* doc_of_row,
-                  int metric, int k, int32_t* out_doc, int32_t* out_row, double* out_score) {
+static int search_impl(const uint16_t* qh, int nq, const uint16_t* corpus, int64_t n, int dim, const int32_t* doc_of_row,
+                       int metric, int k, const double* mod, int32_t* out_doc, int32_t* out_row, double* out_score) {
     int32_t max_doc = -1;
     for (int64_t r = 0; r < n; ++r) {
         int32_t d = doc_of_row ? doc_of_row[r] : (int32_t)r;
@@ -217,6 +217,10 @@ int oracle_search(const uint16_t* qh, int nq, const uint16_t* corpus, int64_t n,
         for (int32_t d = 0; d <= max_doc; ++d) {
             if (rq[d] < 0) continue;
             hit_t h = {bq[d], d, rq[d]};
+            if (mod) { /* modify(closeness of the best chunk): separate multiply and add, as the CUDA merge does */
+                volatile double prod = mod[2 * (size_t)d] * oracle_closeness(bq[d], metric);
+                h.dot = prod + mod[2 * (size_t)d + 1];
+            }
             if (cnt == k && !hit_before(&h, &top[k - 1])) continue;
             int pos = cnt < k ? cnt : k - 1;
             while (pos > 0 && hit_before(&h, &top[pos - 1])) {
@@ -231,7 +235,7 @@ int oracle_search(const uint16_t* qh, int nq, const uint16_t* corpus, int64_t n,
             if (i < cnt) {
                 out_doc[o] = top[i].doc;
                 out_row[o] = top[i].row;
-                out_score[o] = oracle_closeness(top[i].dot, metric);
+                out_score[o] = mod ? top[i].dot : oracle_closeness(top[i].dot, metric);
             } else {
                 out_doc[o] = -1;
                 out_row[o] = -1;
@@ -242,6 +246,57 @@ int oracle_search(const uint16_t* qh, int nq, const uint16_t* corpus, int64_t n,
     }
     free(qf); free(cf); free(best); free(brow);
     return status;
+}
+
+int oracle_search(const uint16_t* qh, int nq, const uint16_t* corpus, int64_t n, int dim, const int32_t* doc_of_row,
+                  int metric, int k, int32_t* out_doc, int32_t* out_row, double* out_score) {
+    return search_impl(qh, nq, corpus, n, dim, doc_of_row, metric, k, NULL, out_doc, out_row, out_score);
+}
+
+/* Score modifiers.  Reference: rank-profile function `modify`
+ * (src/marqo/core/unstructured_vespa_index/unstructured_vespa_schema.py:266-271):
+ *     if (count(mult_weights * attribute(marqo__score_modifiers)) == 0, 1,
+ *         reduce(mult_weights * attribute(marqo__score_modifiers), prod)) * score
+ *     + reduce(add_weights * attribute(marqo__score_modifiers), sum)
+ * with score = closeness(field, marqo__embeddings) (:292-294), i.e. the closeness of the document's BEST chunk.
+ * The tensors are sparse (tensor<double>(p{})): a product cell exists only where the document has the attribute.
+ * attrs: [n_cols][n_docs] doubles, NaN = the document has no such cell.  Terms are evaluated in list order (Vespa
+ * leaves the reduce order unspecified; fp64 keeps the difference far below any score gap the tests use).
+ * out_mod: [n_docs][2] = (mult, add). */
+void oracle_modifiers(const double* attrs, int n_cols, int64_t n_docs, const int32_t* mult_cols, const double* mult_w,
+                      int n_mult, const int32_t* add_cols, const double* add_w, int n_add, double* out_mod) {
+    (void)n_cols;
+    for (int64_t d = 0; d < n_docs; ++d) {
+        double m = 1.0, a = 0.0;
+        int cnt = 0;
+        for (int i = 0; i < n_mult; ++i) {
+            double v = attrs[(size_t)mult_cols[i] * n_docs + d];
+            if (v == v) {
+                volatile double t = mult_w[i] * v;
+                volatile double mm = m * t;
+                m = mm;
+                ++cnt;
+            }
+        }
+        if (cnt == 0) m = 1.0;
+        for (int i = 0; i < n_add; ++i) {
+            double v = attrs[(size_t)add_cols[i] * n_docs + d];
+            if (v == v) {
+                volatile double t = add_w[i] * v;
+                a = a + t;
+            }
+        }
+        out_mod[2 * d] = m;
+        out_mod[2 * d + 1] = a;
+    }
+}
+
+/* oracle_search with modify() applied to every document's best-chunk closeness before the top-k.
+ * mod: [>= max_doc + 1][2] from oracle_modifiers.  out_score is the modified score. */
+int oracle_search_modified(const uint16_t* qh, int nq, const uint16_t* corpus, int64_t n, int dim,
+                           const int32_t* doc_of_row, int metric, int k, const double* mod, int32_t* out_doc,
+                           int32_t* out_row, double* out_score) {
+    return search_impl(qh, nq, corpus, n, dim, doc_of_row, metric, k, mod, out_doc, out_row, out_score);
 }
 
 /* Raw exact dots of one query against a list of rows — used by tests to inspect near-ties. */

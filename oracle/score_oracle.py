@@ -70,6 +70,43 @@ def search_half(qh: np.ndarray, ch: np.ndarray, k: int, metric: str = "prenormal
     return od, orow, osc
 
 
+def modifiers(attrs: np.ndarray, mult: list, add: list) -> np.ndarray:
+    """attrs: float64 [n_cols, n_docs] (NaN = missing cell); mult/add: [(column, weight), ...] -> [n_docs, 2] (mult, add)."""
+    attrs = np.ascontiguousarray(attrs, dtype=np.float64)
+    n_cols, n_docs = attrs.shape
+    mc = np.asarray([c for c, _ in mult], dtype=np.int32)
+    mw = np.asarray([w for _, w in mult], dtype=np.float64)
+    ac = np.asarray([c for c, _ in add], dtype=np.int32)
+    aw = np.asarray([w for _, w in add], dtype=np.float64)
+    out = np.empty((n_docs, 2), np.float64)
+    _lib().oracle_modifiers(_p(attrs), C.c_int(n_cols), C.c_int64(n_docs), _p(mc), _p(mw), C.c_int(len(mult)), _p(ac),
+                            _p(aw), C.c_int(len(add)), _p(out))
+    return out
+
+
+def search_modified(queries: np.ndarray, corpus: np.ndarray, k: int, mod: np.ndarray,
+                    metric: str = "prenormalized-angular", doc_of_row: Optional[np.ndarray] = None):
+    """Exact top-k under modify(closeness) (see oracle_search_modified).  mod: [n_docs, 2] from modifiers()."""
+    m = METRICS[metric]
+    qh = to_half(np.atleast_2d(queries), normalize=(m == 1))
+    ch = to_half(corpus, normalize=(m == 1))
+    nq, dim = qh.shape
+    d = None if doc_of_row is None else np.ascontiguousarray(doc_of_row, dtype=np.int32)
+    ndoc = (int(d.max()) + 1) if d is not None else ch.shape[0]
+    mod = np.ascontiguousarray(mod, dtype=np.float64)
+    assert mod.shape[0] >= ndoc and mod.shape[1] == 2
+    od = np.empty((nq, k), np.int32)
+    orow = np.empty((nq, k), np.int32)
+    osc = np.empty((nq, k), np.float64)
+    lib = _lib()
+    lib.oracle_search_modified.restype = C.c_int
+    st = lib.oracle_search_modified(_p(qh), C.c_int(nq), _p(ch), C.c_int64(ch.shape[0]), C.c_int(dim), _p(d), C.c_int(m),
+                                    C.c_int(k), _p(mod), _p(od), _p(orow), _p(osc))
+    if st != 0:
+        raise MemoryError("oracle_search_modified failed to allocate")
+    return od, orow, osc
+
+
 def closeness(dot: float, metric: str = "prenormalized-angular") -> float:
     return float(_lib().oracle_closeness(C.c_double(dot), C.c_int(METRICS[metric])))
 

@@ -194,6 +194,76 @@ def test_gpu_tensor_index_feed_query_highlights_overwrite_delete(gpu_required):
     ix.close()
 
 
+def test_gpu_tensor_index_score_modifiers(gpu_required):
+    """Tensor search with score_modifiers (tensor_search.py -> vespa_index.py:106-150): the query carries
+    marqo__mult_weights_tensor / marqo__add_weights_tensor, documents carry marqo__score_modifiers."""
+    from marqo_b200.errors import VespaError
+    from marqo_b200.gpu_tensor_index import GpuTensorIndex, gather_documents_from_response
+    rng = np.random.default_rng(11)
+    D, n = 64, 60
+
+    def unit(m):
+        x = rng.standard_normal((m, D)).astype(np.float32)
+        return x / np.linalg.norm(x, axis=1, keepdims=True)
+
+    ix = GpuTensorIndex()
+    vecs, attrs, docs = {}, {}, []
+    for i in range(n):
+        v = unit(int(rng.integers(1, 3)))
+        a = {}
+        if i % 3:
+            a["popularity"] = float(rng.uniform(0.5, 3.0))
+        if i % 2:
+            a["meta.rating"] = float(rng.integers(1, 6))
+        vecs[f"d{i}"], attrs[f"d{i}"] = v, a
+        docs.append(_doc(f"d{i}", {"marqo__id": f"d{i}", "marqo__score_modifiers": a},
+                         {"body": ([f"chunk {j}" for j in range(len(v))], v)}))
+    assert not ix.feed_batch(docs, "s1").errors
+    q = unit(1)[0]
+    qh = q.astype(np.float16).astype(np.float64)
+    mult, add = {"popularity": 1.5, "nobody_has_this": 4.0}, {"meta.rating": 0.02}
+
+    def expected(did):
+        c = float((1.0 / (2.0 - vecs[did].astype(np.float16).astype(np.float64) @ qh)).max())
+        a = attrs[did]
+        m = 1.5 * a["popularity"] if "popularity" in a else 1.0
+        return m * c + 0.02 * a.get("meta.rating", 0.0), c
+
+    qf = {"marqo__query_embedding": q.tolist(), "marqo__mult_weights_tensor": mult, "marqo__add_weights_tensor": add}
+    res = ix.query(_yql("s1", ["body"], 10), hits=10, ranking="embedding_similarity", model_restrict="s1",
+                   query_features=qf)
+    order = sorted(vecs, key=lambda d: (-expected(d)[0], int(d[1:])))[:10]
+    assert [h.id.split("::")[-1] for h in res.hits] == order
+    for h, did in zip(res.hits, order):
+        assert abs(h.relevance - expected(did)[0]) < 1e-9
+        dist = h.dict()["fields"]["matchfeatures"]["distance(field,marqo__embeddings_body)"]
+        assert abs(dist - (1.0 / expected(did)[1] - 1.0)) < 1e-6           # distance() stays the RAW distance
+    assert gather_documents_from_response(res)["hits"][0]["_score"] == res.hits[0].relevance
+    # pre-2.10 index versions use another rank profile name and input names (vespa_index.py:132-136)
+    res29 = ix.query(_yql("s1", ["body"], 10), hits=10, ranking="embedding_similarity_modifiers", model_restrict="s1",
+                     query_features={"marqo__query_embedding": q.tolist(), "marqo__mult_weights": mult,
+                                     "marqo__add_weights": add})
+    assert [h.id for h in res29.hits] == [h.id for h in res.hits]
+    # overwriting a document replaces its modifier cells
+    best = order[0]
+    ix.feed_batch([_doc(best, {"marqo__id": best, "marqo__score_modifiers": {}},
+                        {"body": (["c"], vecs[best][:1])})], "s1")
+    vecs[best], attrs[best] = vecs[best][:1], {}
+    res2 = ix.query(_yql("s1", ["body"], 10), hits=10, ranking="embedding_similarity", model_restrict="s1",
+                    query_features=qf)
+    order2 = sorted(vecs, key=lambda d: (-expected(d)[0], int(d[1:])))[:10]
+    assert [h.id.split("::")[-1] for h in res2.hits] == order2
+    # a negative multiplier cannot be answered exactly for multi-chunk documents: delegate or refuse
+    with pytest.raises(VespaError):
+        ix.query(_yql("s1", ["body"], 10), hits=10, ranking="embedding_similarity", model_restrict="s1",
+                 query_features={"marqo__query_embedding": q.tolist(), "marqo__mult_weights_tensor": {"popularity": -1.0}})
+    # lexical modifier tensors belong to bm25 / hybrid profiles: not a tensor query
+    with pytest.raises(VespaError):
+        ix.query(_yql("s1", ["body"], 10), hits=10, ranking="embedding_similarity", model_restrict="s1",
+                 query_features={"marqo__query_embedding": q.tolist(), "marqo__mult_weights_lexical": {"popularity": 1.0}})
+    ix.close()
+
+
 def test_concurrent_encode_calls_are_serialised_per_handle(gpu_required):
     """Marqo calls encode() from up to 16 request threads with no lock; the handle serialises internally."""
     import threading
