@@ -234,6 +234,35 @@ int b200_model_last_timing(b200_model* m, float* ms, int* launches);
  * out = mean_i(w_i * v_i); if normalize and |out| > 0: out /= |out|.  fp64 arithmetic. */
 int b200_fuse_vectors(const double* vecs, const double* weights, int n, int dim, int normalize, double* out);
 
+/* ===================================================================================== */
+/* Tokenizers: text -> int32 token ids on the host, multi-threaded.       */
+/* ===================================================================================== */
+
+typedef struct b200_tokenizer b200_tokenizer;
+
+/* WordPiece — what AutoTokenizer.from_pretrained(<BERT / e5 checkpoint>) gives the reference
+ * (src/marqo/core/inference/embedding_models/hugging_face_model.py:125-130) and what encode() calls as
+ * tokenizer(sentences, padding=True, truncation=True, max_length=...) (:179-185).  vocab_utf8: the bytes of vocab.txt
+ * (one token per line, id = line number; must contain [PAD] [UNK] [CLS] [SEP]).  do_lower_case != 0 also strips
+ * accents (BertNormalizer's strip_accents=None follows lowercase). */
+int b200_tokenizer_create_wordpiece(const char* vocab_utf8, size_t nbytes, int do_lower_case, b200_tokenizer** out);
+/* CLIP byte-level BPE — open_clip's SimpleTokenizer, the tokenizer OPEN_CLIP.load_tokenizer() returns for non-hf-hub
+ * models (src/marqo/core/inference/embedding_models/open_clip_model.py:211-222; cleaning rules restated at
+ * src/marqo/core/inference/embedding_models/hf_tokenizer.py:9-17).  merges_utf8: the DECOMPRESSED bytes of
+ * bpe_simple_vocab_16e6.txt (line 1 is a header; at most 49152-256-2 merges are used).  ftfy.fix_text is not
+ * restated: text that ftfy would repair (mojibake) tokenises as written. */
+int b200_tokenizer_create_clip_bpe(const char* merges_utf8, size_t nbytes, b200_tokenizer** out);
+int b200_tokenizer_destroy(b200_tokenizer* t);
+int b200_tokenizer_vocab_size(b200_tokenizer* t, int* out_size);
+/* Encode n UTF-8 strings (texts[i], text_bytes[i] bytes; invalid sequences decode as U+FFFD).
+ * WordPiece: "[CLS] ids [SEP]", truncated to max_length, every row padded with [PAD] to the LONGEST row of this call
+ * (padding=True): *out_seq_len = that length <= max_length.  CLIP BPE: "<start_of_text> ids <end_of_text>", truncated
+ * to max_length (= context_length) with the last id forced to <end_of_text>, zero padded: *out_seq_len = max_length.
+ * out_ids / out_mask (mask may be NULL): caller buffers of n * max_length int32; rows are written back to back with
+ * stride *out_seq_len.  max_length >= 2.  Thread-safe (the handle is immutable after creation). */
+int b200_tokenizer_encode(b200_tokenizer* t, const char* const* texts, const int64_t* text_bytes, int n, int max_length,
+                          int32_t* out_ids, int32_t* out_mask, int* out_seq_len);
+
 /* Recommender interpolation: src/marqo/core/utils/vector_interpolation.py —
  * Lerp.interpolate :49-88 (sum_i (w_i / sum w) v_i), Nlerp.interpolate :91-119 (Lerp, then / |.|),
  * Slerp hierarchical :121-193,211-237.  vecs: fp64 [n, dim] host; out: fp64 [dim].  Host-side fp64 arithmetic in

@@ -51,7 +51,7 @@ def _digest(paths: list[Path]) -> str:
 def build_native(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu under csrc/ (one object per file, parallel) and link libmarqo_b200.so."""
     srcs = _sources()
-    deps = srcs + sorted(CSRC.glob("*.cuh")) + [REPO_ROOT / "include" / "marqo_b200.h"]
+    deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc")) + [REPO_ROOT / "include" / "marqo_b200.h"]
     stamp = PKG_DIR / "build" / "stamp"
     digest = _digest(deps)
     if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == digest:
@@ -76,7 +76,7 @@ def build_native(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print("\n".join(log))
     link = [nvcc, "-shared", "-o", str(LIB_PATH), *objs, "-gencode", "arch=compute_100a,code=sm_100a",
-            "-Xcompiler", "-fPIC"]
+            "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -11,9 +11,11 @@ surface on top of the C ABI:
   B200HuggingFace <-> HuggingFaceModel (src/marqo/core/inference/embedding_models/hugging_face_model.py:172-214)
 
 Weights: `model_properties["weights"]` is a state dict (checkpoint names) or a path to one; `"random_init": seed`
-builds seeded random weights (benchmarks / self-test).  Tokenisers: `model_properties["tokenizer"]` is a callable;
-without it the HF loader tries `transformers.AutoTokenizer.from_pretrained(name)` and the CLIP loader
-`open_clip.get_tokenizer` — both need files that only exist where Marqo's own model cache does.
+builds seeded random weights (benchmarks / self-test).  Tokenisers, in order of preference:
+`model_properties["tokenizer"]` (a callable); `model_properties["vocab_file"]` (HF: vocab.txt) /
+`model_properties["merges_file"]` (CLIP: bpe_simple_vocab_16e6.txt[.gz]) -> the C++ tokenizers behind the C ABI
+(marqo_b200/tokenizers.py, §8 f2); else the HF loader tries `transformers.AutoTokenizer.from_pretrained(name)` and the
+CLIP loader `open_clip.get_tokenizer` — both need files that only exist where Marqo's own model cache does.
 """
 from __future__ import annotations
 
@@ -80,6 +82,9 @@ class B200OpenCLIP:
         self.tokenizer = props.get("tokenizer") or self._default_tokenizer()
 
     def _default_tokenizer(self):
+        if self.model_properties.get("merges_file"):
+            from .tokenizers import ClipBpeTokenizer
+            return ClipBpeTokenizer(self.model_properties["merges_file"], context_length=int(self.arch["text"]["ctx"]))
         try:
             import open_clip  # type: ignore
             return open_clip.get_tokenizer(self.model_properties.get("name", "").split("/")[1])
@@ -185,6 +190,10 @@ class B200HuggingFace:
         self._tokenizer = props.get("tokenizer") or self._default_tokenizer()
 
     def _default_tokenizer(self):
+        if self.model_properties.get("vocab_file"):
+            from .tokenizers import WordPieceTokenizer
+            return WordPieceTokenizer(self.model_properties["vocab_file"],
+                                      do_lower_case=bool(self.model_properties.get("do_lower_case", True)))
         try:
             from transformers import AutoTokenizer
             return AutoTokenizer.from_pretrained(self.model_properties["name"])

@@ -108,6 +108,41 @@ def test_vectorise_clip_loader_images_and_text(gpu_required, monkeypatch):
     s2.clear_loaded_models()
 
 
+def test_vectorise_with_cxx_tokenizers(gpu_required, tmp_path):
+    """f2 end to end: model_properties point at vocabulary FILES; strings go through the C++ tokenizers and the CUDA
+    encoders; the expectation tokenises with the oracle tokenizers (HF `tokenizers` / restated SimpleTokenizer)."""
+    from marqo_b200 import s2_inference as s2, weights as Wt
+    from oracle import tokenizers as OT
+    s2.clear_loaded_models()
+    # ---- BERT + WordPiece
+    words = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + [f"w{i}" for i in range(600)] + \
+            ["##ing", "##s", "##ed", ",", ".", "!", "caf", "##e", "cafe"]
+    vocab_file = tmp_path / "vocab.txt"
+    vocab_file.write_text("\n".join(words) + "\n", encoding="utf-8")
+    props = {"name": "tiny-bert-wp", "dimensions": 128, "type": "hf", "tokens": 32, "arch": TINY_BERT_ARCH,
+             "random_init": 77, "vocab_file": str(vocab_file)}
+    sentences = ["w1 w2 w3ing, w4s!", "Café W5 w599ed unknownword.", "w7", "w8 " * 60]
+    out = s2.vectorise("tiny-bert-wp", sentences, model_properties=props, device="cuda:0", normalize_embeddings=True)
+    ids, mask = OT.bert_encode_batch(OT.bert_wordpiece(words), sentences, 32)
+    sd = {k: torch.from_numpy(v) for k, v in Wt.random_bert_weights(TINY_BERT_ARCH, 77).items()}
+    ref = E.bert_encode(sd, E.BertCfg(128, 2, 2, 512, vocab=1000, max_pos=64), torch.from_numpy(ids), torch.from_numpy(mask))
+    _cos_ok(out, ref)
+    # ---- CLIP text tower + byte-level BPE
+    corpus = ["a photo of a cat", "a photo of a dog", "the quick brown fox", "hello world, it's me"] * 2
+    merges = OT.train_toy_merges(corpus, 300)
+    merges_file = tmp_path / "bpe.txt"
+    merges_file.write_text(merges, encoding="utf-8")
+    cprops = {"name": "open_clip/tiny/test", "dimensions": 128, "type": "open_clip", "arch": TINY_CLIP_ARCH,
+              "random_init": 5, "merges_file": str(merges_file)}
+    texts = ["A photo of a CAT", "hello &amp; world", "the quick brown dog's photo " * 20]
+    got = s2.vectorise("open_clip/tiny/test", texts, model_properties=cprops, device="cuda:0")
+    tok_ids = OT.SimpleTokenizerOracle(merges)(texts)
+    assert tok_ids.max() < TINY_CLIP_ARCH["text"]["vocab"]
+    csd = {k: torch.from_numpy(v) for k, v in Wt.random_clip_weights(TINY_CLIP_ARCH, 5).items()}
+    s2.clear_loaded_models()
+    _cos_ok(got, E.clip_encode_text(csd, E.tiny_clip(), torch.from_numpy(tok_ids)))
+
+
 def _doc(doc_id, fields, embs):
     f = dict(fields)
     for name, (chunks, vecs) in embs.items():
