@@ -34,3 +34,30 @@ out = {"n": n, "d": d, "scan_ms_med": scan[len(scan)//2], "scan_ms_min": scan[0]
        "GBps_med": bytes_ / scan[len(scan)//2] / 1e6, "GBps_best": bytes_ / scan[0] / 1e6, "all": res}
 print(json.dumps(out))
 print(od[:2].tolist(), osc[:2].tolist())
+
+# score modifiers (f3): same corpus, 3 attribute columns, the scan kernel's HAS_MOD variant through the host entry point
+if len(sys.argv) > 3 and sys.argv[3] == "mod":
+    rng = np.random.default_rng(0)
+    ids = np.arange(n, dtype=np.int32)
+    for c in range(3):
+        store.set_attributes(c, ids, rng.uniform(0.5, 2.0, size=n))
+    qh = q.cpu().numpy()
+    for nq_m in (1, 64):
+        ts = []
+        for it in range(6):
+            t0 = time.perf_counter()
+            store.search_modified(qh[:nq_m], k, [(0, 1.5), (1, 0.5)], [(2, 0.01)])
+            wall = (time.perf_counter() - t0) * 1e3
+            ts.append((store.last_timing()[0], wall))
+        ts = sorted(ts[2:])
+        print(json.dumps({"modified_search": True, "nq": nq_m, "scan_ms_med": ts[len(ts) // 2][0],
+                          "GBps_med": bytes_ / ts[len(ts) // 2][0] / 1e6, "wall_ms_med": sorted(w for _, w in ts)[len(ts) // 2]}))
+    for nq_m in (1, 64):
+        ts = []
+        for it in range(6):
+            t0 = time.perf_counter()
+            store.search(qh[:nq_m], k)
+            ts.append((store.last_timing()[0], (time.perf_counter() - t0) * 1e3))
+        ts = sorted(ts[2:])
+        print(json.dumps({"modified_search": False, "nq": nq_m, "scan_ms_med": ts[len(ts) // 2][0],
+                          "wall_ms_med": sorted(w for _, w in ts)[len(ts) // 2]}))
