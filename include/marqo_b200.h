@@ -294,6 +294,8 @@ int b200_debug_gemm(int device, const float* A, const float* W, const float* bia
 int b200_debug_attention(int device, const float* qkv, int B, int S, int W, int H, int mask, const int32_t* kv_len,
                          float* out);
 /* LayerNorm over rows of fp32 [rows, w]. */
+/* Mean device time (ms, CUDA events) of `iters` back-to-back attention launches on device-generated data. */
+int b200_debug_attention_time(int device, int B, int S, int W, int H, int mask, int iters, float* out_ms);
 int b200_debug_layernorm(int device, const float* x, const float* gamma, const float* beta, float eps, int rows, int w,
                          float* out);
 /* Pillow-compatible bicubic resize (shortest side -> S) + centre crop of uint8 HWC images [n,h,w,3] -> [n,S,S,3]. */

@@ -43,6 +43,17 @@ __global__ void bf16_to_f32_kernel(const __nv_bfloat16* src, float* dst, long lo
     if (i < n) dst[i] = __bfloat162float(src[i]);
 }
 
+// pseudo-random bf16 values in [-1, 1) (kernel timing probes: no 200 MB host upload)
+__global__ void fill_bf16_kernel(__nv_bfloat16* dst, long long n, uint32_t seed) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = (uint32_t)i * 2654435761u + seed;
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    dst[i] = __float2bfloat16_rn((float)(x & 0xFFFF) / 32768.0f - 1.0f);
+}
+
 void require_device(int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
@@ -113,6 +124,38 @@ int b200_debug_attention(int device, const float* qkv, int B, int S, int W, int 
         MB_CUDA(cudaGetLastError());
         MB_CUDA(cudaStreamSynchronize(sc.s));
         MB_CUDA(cudaMemcpy(out, dOut, M * W * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int b200_debug_attention_time(int device, int B, int S, int W, int H, int mask, int iters, float* out_ms) {
+    return guarded([&] {
+        MB_CHECK_ARG(out_ms != nullptr, "NULL buffer");
+        MB_CHECK_ARG(B > 0 && S > 0 && W > 0 && H > 0 && iters > 0, "B, S, W, H, iters must be positive");
+        require_device(device);
+        DeviceGuard g(device);
+        Scratch sc;
+        MB_CUDA(cudaStreamCreate(&sc.s));
+        const size_t M = (size_t)B * S;
+        __nv_bfloat16* dq = sc.alloc<__nv_bfloat16>(M * 3 * W);
+        __nv_bfloat16* dO = sc.alloc<__nv_bfloat16>(M * W);
+        const long long n = (long long)(M * 3 * W);
+        fill_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sc.s>>>(dq, n, 12345u);
+        MB_CUDA(cudaGetLastError());
+        std::vector<int32_t> lens((size_t)B, S);
+        const int32_t* dlen = mask == attention::MASK_KEYLEN ? sc.upload(lens.data(), (size_t)B) : nullptr;
+        cudaEvent_t e0, e1;
+        MB_CUDA(cudaEventCreate(&e0));
+        MB_CUDA(cudaEventCreate(&e1));
+        for (int i = 0; i < 3; ++i) attention::launch(dq, dO, B, S, W, H, mask, dlen, sc.s);   // warm-up
+        MB_CUDA(cudaEventRecord(e0, sc.s));
+        for (int i = 0; i < iters; ++i) attention::launch(dq, dO, B, S, W, H, mask, dlen, sc.s);
+        MB_CUDA(cudaEventRecord(e1, sc.s));
+        MB_CUDA(cudaStreamSynchronize(sc.s));
+        float ms = 0.f;
+        MB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *out_ms = ms / (float)iters;
     });
 }
 

@@ -212,6 +212,13 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+// named barrier among COUNT threads (COUNT % 32 == 0); id 0 is __syncthreads().  The id must be an immediate: with a
+// register id ptxas reserves all 16 hardware barriers for the CTA, and an SM only has 16 to share between its CTAs.
+template <int ID, int COUNT>
+__device__ __forceinline__ void bar_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+}
+
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <uint32_t NCOLS>
