@@ -29,12 +29,17 @@ constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int THREADS = 224;   // warp 0 TMA, warp 1 MMA, warps 2-5 softmax, warp 6 remainder rows
 constexpr int KV_STAGES = 2;
-constexpr int TAIL_INLINE_MAX = 2;   // remainder query rows handled inside the main kernel (more: second kernel)
+constexpr int TAIL_INLINE_MAX = 1;   // remainder query rows handled inside the main kernel
 constexpr uint32_t Q_BYTES = BQ * HD * 2;        // 16 KB
 constexpr uint32_t KV_TILE_BYTES = BKV * HD * 2;  // 16 KB each for K and V
 constexpr uint32_t P_BYTES = BQ * BKV * 2;        // 32 KB (two 64-key K-major chunks)
-constexpr uint32_t TAILQ_BYTES = TAIL_INLINE_MAX * HD * 2;   // the remainder rows' queries
-constexpr uint32_t SMEM_BYTES = Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES + 128 + TAILQ_BYTES;
+constexpr uint32_t TAILQ_BYTES = TAIL_INLINE_MAX * HD * 2;   // the remainder row's query
+constexpr uint32_t TAILS_BYTES = BQ * 4;                     // the remainder key's score for each of the 128 rows
+constexpr uint32_t TAILV_BYTES = HD * 2;                     // the remainder key's V row
+// 115712 B: two CTAs (+ 1 KB of system-reserved smem each) fill the SM's 228 KB exactly
+constexpr uint32_t SMEM_BYTES =
+    Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES + 128 + TAILQ_BYTES + TAILS_BYTES + TAILV_BYTES + 128;
+static_assert(SMEM_BYTES <= 115712, "two CTAs per SM");
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t S_COL = 0, O_COL = 128;
 
@@ -42,6 +47,25 @@ __device__ __forceinline__ float ex2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(ptx::smem_u32(p)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(ptx::smem_u32(p)));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+                 "{%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
 }
 
 // Query rows that do not fill a 128-row tile (e.g. row 256 of a 257-token ViT sequence): one warp per
@@ -179,8 +203,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
     uint64_t* p_full = bars + 7;
     uint64_t* pv_done = bars + 8;
     uint64_t* q_empty = bars + 9;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+    uint64_t* tail_full = bars + 10;    // the remainder key's scores + V row are staged (warp 6 -> softmax warps)
+    uint64_t* tail_empty = bars + 11;   // ... and have been consumed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
     __nv_bfloat16* sTailQ = reinterpret_cast<__nv_bfloat16*>(sP + P_BYTES + 128);
+    float* sTailS = reinterpret_cast<float*>(sP + P_BYTES + 128 + TAILQ_BYTES);
+    __nv_bfloat16* sTailV = reinterpret_cast<__nv_bfloat16*>(sP + P_BYTES + 128 + TAILQ_BYTES + TAILS_BYTES);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -189,7 +217,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap);
         ptx::mbar_init(q_full, 1);
-        ptx::mbar_init(q_empty, 1);
+        ptx::mbar_init(q_empty, 2);   // the MMA warp's commit after the item's last S + warp 6 (remainder-key scores)
+        ptx::mbar_init(tail_full, 1);
+        ptx::mbar_init(tail_empty, 4);
         for (int i = 0; i < KV_STAGES; ++i) {
             ptx::mbar_init(&kv_full[i], 1);
             ptx::mbar_init(&kv_empty[i], 2);   // the MMA warp's commit + the remainder-row warp
@@ -236,186 +266,284 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         }
     } else if (warp == 1) {
         // ================================================================== MMA issuer
+        // Two cursors walk the same (item, key block) sequence: S of block g + 1 is issued BEFORE P.V of block g, so
+        // the tensor core computes the next scores while the softmax warps are still rescaling O and storing P — and,
+        // at an item boundary, while they run the epilogue.
         constexpr uint32_t idesc_s = ptx::make_idesc_f16_major(1, BQ, BKV, 0, 0);
         constexpr uint32_t idesc_o = ptx::make_idesc_f16_major(1, BQ, HD, 0, 1);  // B (= V) is MN-major
-        uint32_t n = 0, g = 0;
+        struct Cursor {
+            int it, j, nkb;
+            uint32_t n;
+        };
+        // skip to the first item (from c.it on) that has key blocks; items without any only hand Q back
+        auto settle = [&](Cursor& c, bool owns_q) {
+            while (c.it < total_items) {
+                const Item w = decode_item(c.it, q_blocks, H);
+                int len, kend;
+                item_extent<MASK>(w, S, s_main, kv_len, len, kend, c.nkb);
+                if (c.nkb > 0) return;
+                if (owns_q) {
+                    ptx::mbar_wait(q_full, c.n & 1);
+                    if (lane == 0) ptx::mbar_arrive(q_empty);   // nothing to multiply: release Q right away
+                    __syncwarp();
+                }
+                c.it += gridDim.x;
+                ++c.n;
+            }
+        };
+        auto advance = [&](Cursor& c, bool owns_q) {
+            if (++c.j == c.nkb) {
+                c.j = 0;
+                c.it += gridDim.x;
+                ++c.n;
+                settle(c, owns_q);
+            }
+        };
+        Cursor cs{(int)blockIdx.x, 0, 0, 0u}, cp{(int)blockIdx.x, 0, 0, 0u};
+        settle(cs, true);
+        settle(cp, false);
+        uint32_t gs = 0, gp = 0;   // key blocks whose S / P.V have been issued
+        auto issue_s = [&]() {
+            if (cs.j == 0) ptx::mbar_wait(q_full, cs.n & 1);
+            const int st = gs & 1;
+            ptx::mbar_wait(&kv_full[st], (gs >> 1) & 1);
+            if (gs > 0) ptx::mbar_wait(s_free, (gs - 1) & 1);  // softmax has finished reading S of the previous block
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                const uint32_t q_base = ptx::smem_u32(sQ);
+                const uint32_t k_base = ptx::smem_u32(sKV + (size_t)st * 2 * KV_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k)
+                    ptx::umma_f16(tmem_base + S_COL, ptx::make_desc_k_sw128(q_base + k * 32),
+                                  ptx::make_desc_k_sw128(k_base + k * 32), idesc_s, k != 0 ? 1u : 0u);
+                ptx::umma_commit(s_full);
+                if (cs.j == cs.nkb - 1) ptx::umma_commit(q_empty);   // Q may be overwritten once these MMAs are done
+            }
+            __syncwarp();
+            ++gs;
+            advance(cs, true);
+        };
+        if (cs.it < total_items) issue_s();
+        while (cp.it < total_items) {
+            if (cs.it < total_items) issue_s();
+            const int st = gp & 1;
+            ptx::mbar_wait(p_full, gp & 1);  // P of this block is in smem and O has been rescaled
+            ptx::tc_fence_after();
+            if (lane == 0) {
+                const uint32_t p_base = ptx::smem_u32(sP);
+                const uint32_t v_base = ptx::smem_u32(sKV + (size_t)st * 2 * KV_TILE_BYTES) + KV_TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BKV / 16; ++k) {
+                    const uint32_t a_addr = p_base + (k >> 2) * (BQ * 128) + (k & 3) * 32;
+                    const uint32_t b_addr = v_base + k * 16 * 128;  // 16 keys = two 8-key swizzle atoms
+                    ptx::umma_f16(tmem_base + O_COL, ptx::make_desc_k_sw128(a_addr),
+                                  ptx::make_desc_mn_sw128(b_addr, 8192, 1024), idesc_o, (cp.j | k) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&kv_empty[st]);
+                ptx::umma_commit(pv_done);
+            }
+            __syncwarp();
+            ++gp;
+            advance(cp, false);
+        }
+    } else if (warp == 6) {
+        // ================================================================== remainder key + remainder query row
+        // (S = k * 128 + 1, e.g. the 257 tokens of ViT-L-14).  In every item this warp
+        //   * scores the remainder KEY against the item's 128 query rows straight from the Q tile in shared memory and
+        //     stages the scores + the key's V row for the softmax warps' epilogue (which then touches no global memory
+        //     besides its output), and
+        //   * is the second consumer of the K / V ring (kv_empty counts two arrivals);
+        // in the items of the LAST query block it also computes the remainder ROW against the K / V tiles while they
+        // sit in shared memory, with warp-level mma.sync (m16n8k16, row 0 of a 16-row tile) — a scalar version of this
+        // took ~11 us per item and throttled the whole ring.
+        uint32_t g = 0, n = 0, nt_staged = 0;   // key blocks, items, remainder-key stagings so far
+        const size_t ld = (size_t)3 * W;
+        const int gq = lane >> 2, tq = lane & 3;   // mma fragment coordinates: row group, column pair
         for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n) {
             const Item w = decode_item(it, q_blocks, H);
             int len, kend, nkb;
             item_extent<MASK>(w, S, s_main, kv_len, len, kend, nkb);
-            ptx::mbar_wait(q_full, n & 1);
-            for (int j = 0; j < nkb; ++j, ++g) {
-                const int st = g & 1;
-                const uint32_t par = g & 1;
-                ptx::mbar_wait(&kv_full[st], (g >> 1) & 1);
-                if (g > 0) ptx::mbar_wait(s_free, par ^ 1);  // softmax has finished reading S of the previous block
-                ptx::tc_fence_after();
-                const uint32_t k_base = ptx::smem_u32(sKV + (size_t)st * 2 * KV_TILE_BYTES);
-                const uint32_t v_base = k_base + KV_TILE_BYTES;
-                if (lane == 0) {
-                    const uint32_t q_base = ptx::smem_u32(sQ);
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        ptx::umma_f16(tmem_base + S_COL, ptx::make_desc_k_sw128(q_base + k * 32),
-                                      ptx::make_desc_k_sw128(k_base + k * 32), idesc_s, k != 0 ? 1u : 0u);
-                    ptx::umma_commit(s_full);
-                    if (j == nkb - 1) ptx::umma_commit(q_empty);   // Q may be overwritten once these MMAs are done
-                }
-                __syncwarp();
-                ptx::mbar_wait(p_full, par);  // P_j is in smem and O has been rescaled
-                ptx::tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t p_base = ptx::smem_u32(sP);
-#pragma unroll
-                    for (int k = 0; k < BKV / 16; ++k) {
-                        const uint32_t a_addr = p_base + (k >> 2) * (BQ * 128) + (k & 3) * 32;
-                        const uint32_t b_addr = v_base + k * 16 * 128;  // 16 keys = two 8-key swizzle atoms
-                        ptx::umma_f16(tmem_base + O_COL, ptx::make_desc_k_sw128(a_addr),
-                                      ptx::make_desc_mn_sw128(b_addr, 8192, 1024), idesc_o, (j | k) != 0 ? 1u : 0u);
-                    }
-                    ptx::umma_commit(&kv_empty[st]);
-                    ptx::umma_commit(pv_done);
-                }
-                __syncwarp();
-            }
-            if (nkb == 0 && lane == 0) ptx::mbar_arrive(q_empty);   // nothing to multiply: release Q right away
-            __syncwarp();
-        }
-    } else if (warp == 6) {
-        // ================================================================== remainder query rows (S = k*128 + r)
-        // In the items of the LAST query block this warp computes the r <= 2 remainder rows against the K / V tiles
-        // while they sit in shared memory (instead of a second kernel re-reading K and V); in every item it is the
-        // second consumer of the ring (kv_empty counts two arrivals).
-        uint32_t g = 0;
-        const size_t ld = (size_t)3 * W;
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-            const Item w = decode_item(it, q_blocks, H);
-            int len, kend, nkb;
-            item_extent<MASK>(w, S, s_main, kv_len, len, kend, nkb);
             const int row_base = w.b * S;
-            const int rows = (inline_tail_rows > 0 && w.qb == q_blocks - 1) ? inline_tail_rows : 0;
-            float m_t[TAIL_INLINE_MAX], l_t[TAIL_INLINE_MAX], ox[TAIL_INLINE_MAX], oy[TAIL_INLINE_MAX];
+            const bool do_row = inline_tail_rows > 0 && w.qb == q_blocks - 1;
+            const int trow = s_main;   // the remainder row / key index
+            ptx::mbar_wait(q_full, n & 1);
+            if (s_main < len) {
+                const __nv_bfloat16* krow = qkv + ((size_t)row_base + s_main) * ld + W + w.h * HD;
+                uint4 k4[HD / 8];
 #pragma unroll
-            for (int tr = 0; tr < TAIL_INLINE_MAX; ++tr) {
-                m_t[tr] = -INFINITY;
-                l_t[tr] = 0.f;
-                ox[tr] = 0.f;
-                oy[tr] = 0.f;
+                for (int u = 0; u < HD / 8; ++u) k4[u] = __ldg(reinterpret_cast<const uint4*>(krow) + u);
+                const __nv_bfloat162 v2 = reinterpret_cast<const __nv_bfloat162*>(krow + W)[lane];
+                {
+                    const int nxt = it + gridDim.x;
+                    if (lane == 0 && nxt < total_items) {   // the next item's remainder rows: into L2 ahead of time
+                        const Item wn = decode_item(nxt, q_blocks, H);
+                        const __nv_bfloat16* nrow = qkv + ((size_t)wn.b * S + s_main) * ld + W + wn.h * HD;
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + W));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow - W));
+                    }
+                }
+                if (nt_staged > 0) ptx::mbar_wait(tail_empty, (nt_staged - 1) & 1);   // previous staging consumed
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int r = lane + 32 * i;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int u = 0; u < HD / 8; ++u) {
+                        const uint4 q4 = *reinterpret_cast<const uint4*>(sQ + (size_t)r * 128 + ((u ^ (r & 7)) << 4));
+                        const uint32_t qq[4] = {q4.x, q4.y, q4.z, q4.w};
+                        const uint32_t kk[4] = {k4[u].x, k4[u].y, k4[u].z, k4[u].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 qa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[e]));
+                            const float2 ka = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk[e]));
+                            acc = fmaf(qa.x, ka.x, acc);
+                            acc = fmaf(qa.y, ka.y, acc);
+                        }
+                    }
+                    sTailS[r] = acc * scale_log2e;
+                }
+                reinterpret_cast<__nv_bfloat162*>(sTailV)[lane] = v2;
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tail_full);
+                ++nt_staged;
             }
-            if (rows > 0) {
-                __syncwarp();
-                for (int tr = 0; tr < rows; ++tr)   // 64 bf16 per row: one bf16x2 per lane
-                    reinterpret_cast<__nv_bfloat162*>(sTailQ)[tr * 32 + lane] = reinterpret_cast<const __nv_bfloat162*>(
-                        qkv + ((size_t)row_base + s_main + tr) * ld + w.h * HD)[lane];
-                __syncwarp();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(q_empty);   // this warp no longer needs the Q tile
+
+            // ---- remainder row: A fragments of a 16-row tile whose row 0 is the query, rows 1..15 zero
+            uint32_t qf[4][4];
+            float o[8][4];
+            float row_max = -INFINITY, row_sum = 0.f;   // row 0 lives in the lanes with gq == 0
+            int tlimit = len;                           // keys >= tlimit are masked for the remainder row
+            if (MASK == MASK_CAUSAL) tlimit = min(tlimit, trow + 1);
+            if (do_row) {
+                const __nv_bfloat16* qrow_p = qkv + ((size_t)row_base + trow) * ld + w.h * HD;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    qf[ks][0] = gq == 0 ? *reinterpret_cast<const uint32_t*>(qrow_p + ks * 16 + 2 * tq) : 0u;
+                    qf[ks][1] = 0u;
+                    qf[ks][2] = gq == 0 ? *reinterpret_cast<const uint32_t*>(qrow_p + ks * 16 + 8 + 2 * tq) : 0u;
+                    qf[ks][3] = 0u;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[i][e] = 0.f;
             }
             for (int j = 0; j < nkb; ++j, ++g) {
                 const int st = g & 1;
                 ptx::mbar_wait(&kv_full[st], (g >> 1) & 1);
-                if (rows > 0) {
-                    const uint8_t* kt = sKV + (size_t)st * 2 * KV_TILE_BYTES;
-                    const uint8_t* vt = kt + KV_TILE_BYTES;
+                if (do_row) {
+                    const __nv_bfloat16* kt = reinterpret_cast<const __nv_bfloat16*>(sKV + (size_t)st * 2 * KV_TILE_BYTES);
+                    const __nv_bfloat16* vt = kt + BKV * HD;
+                    const int mat = lane >> 3, rr8 = lane & 7;
+                    auto tile_at = [](const __nv_bfloat16* tile, int row, int chunk) {
+                        return tile + row * HD + ((chunk ^ (row & 7)) << 3);   // 128B-swizzled 16-byte chunks
+                    };
+                    // S = q K^T for the 128 keys of the block: 16 n-tiles of 8 keys
+                    float sc[16][4];
 #pragma unroll
-                    for (int tr = 0; tr < TAIL_INLINE_MAX; ++tr) {
-                        if (tr >= rows) continue;
-                        const int trow = s_main + tr;
-                        int tlimit = len;                               // keys >= tlimit are masked for this row
-                        if (MASK == MASK_CAUSAL) tlimit = min(tlimit, trow + 1);
-                        const uint4* q4p = reinterpret_cast<const uint4*>(sTailQ + tr * HD);
-                        float sc[4];
-                        float bm = -INFINITY;
+                    for (int i = 0; i < 16; ++i)
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int key = lane + 32 * i;   // row & 7 == lane & 7: the 8 swizzled units spread over the banks
-                            float acc = 0.f;
-#pragma unroll 2
-                            for (int u = 0; u < 8; ++u) {
-                                const uint4 k4 = *reinterpret_cast<const uint4*>(kt + key * 128 + ((u ^ (key & 7)) << 4));
-                                const uint4 q4 = q4p[u];   // same address in every lane: broadcast
-                                const uint32_t kw[4] = {k4.x, k4.y, k4.z, k4.w};
-                                const uint32_t qw[4] = {q4.x, q4.y, q4.z, q4.w};
+                        for (int e = 0; e < 4; ++e) sc[i][e] = 0.f;
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 kf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kw[e]));
-                                    const float2 qf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qw[e]));
-                                    acc = fmaf(qf.x, kf.x, acc);
-                                    acc = fmaf(qf.y, kf.y, acc);
-                                }
-                            }
-                            acc *= scale_log2e;
-                            const int gkey = j * BKV + key;
-                            sc[i] = (gkey < tlimit && gkey < s_main) ? acc : -INFINITY;
-                            bm = fmaxf(bm, sc[i]);
+                    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                        for (int np = 0; np < 8; ++np) {
+                            uint32_t kf[4];
+                            ldmatrix_x4(kf, tile_at(kt, np * 16 + (mat >> 1) * 8 + rr8, ks * 2 + (mat & 1)));
+                            mma_bf16(sc[2 * np], qf[ks], kf[0], kf[1]);
+                            mma_bf16(sc[2 * np + 1], qf[ks], kf[2], kf[3]);
                         }
+                    }
+                    // mask + scale (log2 domain) + online softmax of row 0 (elements 0, 1 of every fragment)
+                    float mx = row_max;
 #pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, off));
-                        const float m_new = fmaxf(m_t[tr], bm);
-                        const float m_safe = m_new == -INFINITY ? 0.f : m_new;
-                        const float alpha = ex2(m_t[tr] - m_safe);
-                        float pb[4];
-                        float ls = 0.f;
+                    for (int i = 0; i < 16; ++i) {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float pe = sc[i] == -INFINITY ? 0.f : ex2(sc[i] - m_safe);
-                            ls += pe;
-                            pb[i] = __bfloat162float(__float2bfloat16_rn(pe));   // same P rounding as the MMA path
+                        for (int e = 0; e < 2; ++e) {
+                            const int key = j * BKV + i * 8 + 2 * tq + e;
+                            const float v = (key < tlimit && key < s_main) ? sc[i][e] * scale_log2e : -INFINITY;
+                            sc[i][e] = v;
+                            mx = fmaxf(mx, v);
                         }
+                    }
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+                    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+                    const float msafe = mx == -INFINITY ? 0.f : mx;
+                    const float corr = ex2(row_max - msafe);   // 0 on the first block
+                    row_max = mx;
+                    row_sum *= corr;
 #pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) ls += __shfl_xor_sync(0xffffffffu, ls, off);
-                        l_t[tr] = l_t[tr] * alpha + ls;
-                        float axx = ox[tr] * alpha, ayy = oy[tr] * alpha;
-                        m_t[tr] = m_new;
+                    for (int i = 0; i < 8; ++i) {
+                        o[i][0] *= corr;
+                        o[i][1] *= corr;
+                    }
+                    float ps = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-#pragma unroll 8
-                            for (int src = 0; src < 32; ++src) {
-                                const int key = src + 32 * i;
-                                const float pk = __shfl_sync(0xffffffffu, pb[i], src);
-                                const __nv_bfloat162 v2 = *reinterpret_cast<const __nv_bfloat162*>(
-                                    vt + key * 128 + (((lane >> 2) ^ (key & 7)) << 4) + (lane & 3) * 4);
-                                const float2 vf = __bfloat1622float2(v2);
-                                axx = fmaf(pk, vf.x, axx);
-                                ayy = fmaf(pk, vf.y, ayy);
-                            }
+                    for (int i = 0; i < 16; ++i) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const float pv = ex2(sc[i][e] - msafe);   // exp2(-inf) = 0 for masked keys
+                            ps += pv;
+                            sc[i][e] = pv;
                         }
-                        ox[tr] = axx;
-                        oy[tr] = ayy;
+                    }
+                    row_sum += ps;
+                    // O += P V: 8 k-steps of 16 keys, 8 n-tiles of 8 dims; rows 8..15 of P are zero
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks) {
+                        uint32_t pa[4];
+                        pa[0] = pack2(sc[2 * ks][0], sc[2 * ks][1]);
+                        pa[1] = 0u;
+                        pa[2] = pack2(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
+                        pa[3] = 0u;
+#pragma unroll
+                        for (int dp = 0; dp < 4; ++dp) {
+                            uint32_t vf[4];
+                            ldmatrix_x4_trans(vf, tile_at(vt, ks * 16 + (mat & 1) * 8 + rr8, dp * 2 + (mat >> 1)));
+                            mma_bf16(o[2 * dp], pa, vf[0], vf[1]);
+                            mma_bf16(o[2 * dp + 1], pa, vf[2], vf[3]);
+                        }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&kv_empty[st]);
             }
-            if (rows > 0) {
+            if (do_row) {
+                // the remainder key against the remainder row (global memory; lanes over the 64 dims, warp-reduced)
+                if (s_main < tlimit) {
+                    const __nv_bfloat16* qrow_p = qkv + ((size_t)row_base + trow) * ld + w.h * HD;
+                    const __nv_bfloat16* krow = qkv + ((size_t)row_base + s_main) * ld + W + w.h * HD;
+                    const float2 qpair = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(qrow_p)[lane]);
+                    const float2 kf2 = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(krow)[lane]);
+                    float sd = qpair.x * kf2.x + qpair.y * kf2.y;
 #pragma unroll
-                for (int tr = 0; tr < TAIL_INLINE_MAX; ++tr) {
-                    if (tr >= rows) continue;
-                    const int trow = s_main + tr;
-                    int tlimit = len;
-                    if (MASK == MASK_CAUSAL) tlimit = min(tlimit, trow + 1);
-                    const float2 qpair = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(sTailQ)[tr * 32 + lane]);
-                    float m_r = m_t[tr], l_r = l_t[tr], axx = ox[tr], ayy = oy[tr];
-                    // remainder keys from global memory (lanes over the 64 dims, warp-reduced dot)
-                    for (int key = s_main; key < tlimit; ++key) {
-                        const float2 kf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(
-                            qkv + ((size_t)row_base + key) * ld + W + w.h * HD)[lane]);
-                        const float2 vf = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(
-                            qkv + ((size_t)row_base + key) * ld + 2 * W + w.h * HD)[lane]);
-                        float sd = qpair.x * kf.x + qpair.y * kf.y;
+                    for (int off = 16; off > 0; off >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, off);
+                    const float scv = sd * scale_log2e;
+                    const float m_new = fmaxf(row_max, scv);
+                    const float alpha = ex2(row_max - m_new);
+                    const float pe = ex2(scv - m_new);
+                    const float pbv = __bfloat162float(__float2bfloat16_rn(pe));   // P is bf16 in the MMA path too
+                    row_sum = row_sum * alpha + (tq == 0 ? pe : 0.f);               // row_sum is a per-quad partial
+                    row_max = m_new;
 #pragma unroll
-                        for (int off = 16; off > 0; off >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, off);
-                        const float scv = sd * scale_log2e;
-                        const float m_new = fmaxf(m_r, scv);
-                        const float alpha = ex2(m_r - m_new);
-                        const float pe = ex2(scv - m_new);
-                        const float pbv = __bfloat162float(__float2bfloat16_rn(pe));
-                        l_r = l_r * alpha + pe;
-                        axx = fmaf(axx, alpha, pbv * vf.x);
-                        ayy = fmaf(ayy, alpha, pbv * vf.y);
-                        m_r = m_new;
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 vf2 = __bfloat1622float2(
+                            *reinterpret_cast<const __nv_bfloat162*>(krow + W + i * 8 + 2 * tq));
+                        o[i][0] = fmaf(o[i][0], alpha, pbv * vf2.x);
+                        o[i][1] = fmaf(o[i][1], alpha, pbv * vf2.y);
                     }
-                    const float inv_t = l_r > 0.f ? 1.f / l_r : 0.f;
-                    reinterpret_cast<__nv_bfloat162*>(out + ((size_t)row_base + trow) * W + w.h * HD)[lane] =
-                        __floats2bfloat162_rn(axx * inv_t, ayy * inv_t);
+                }
+                row_sum += __shfl_xor_sync(0xffffffffu, row_sum, 1);
+                row_sum += __shfl_xor_sync(0xffffffffu, row_sum, 2);
+                const float inv_t = row_sum > 0.f ? 1.f / row_sum : 0.f;
+                if (gq == 0) {
+                    __nv_bfloat16* orow = out + ((size_t)row_base + trow) * W + w.h * HD;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        *reinterpret_cast<uint32_t*>(orow + i * 8 + 2 * tq) = pack2(o[i][0] * inv_t, o[i][1] * inv_t);
                 }
             }
         }
@@ -424,7 +552,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         const int sp = warp & 3;
         const int r = sp * 32 + lane;  // row within the tile == TMEM lane
         const uint32_t lane_addr = tmem_base + (uint32_t(sp * 32) << 16);
-        uint32_t g = 0;
+        uint32_t g = 0, nt = 0;   // key blocks / remainder-key stagings consumed so far
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const Item w = decode_item(it, q_blocks, H);
             int len, kend, nkb;
@@ -433,28 +561,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
             const int qrow = w.q0 + r;     // position in the sequence
             const int h = w.h;
             float m_run = -INFINITY, l_run = 0.f;
-            // Tail keys (the <= 2 keys past the last full block) are folded in on the CUDA cores in the epilogue.  Their
-            // K / V rows (the same for every thread, never touched by the TMA boxes) are pulled into L1 now and — for
-            // the item this CTA will process NEXT — into L2, so that the epilogue does not sit on a DRAM round trip.
-            constexpr int TAIL_KEYS_MAX = 2;   // == launch_tc's TAIL_MAX
+            // The remainder key (257 = 2 * 128 + 1) is folded in on the CUDA cores in the epilogue from the scores and
+            // the V row that warp 6 stages in shared memory.
+            const bool has_tail_key = s_main < len;   // uniform over the CTA
             const int tail_end = qrow < S ? (MASK == MASK_CAUSAL ? min(len, qrow + 1) : len) : 0;
-            const size_t ld = (size_t)3 * W;
-            if (lane == 0 && s_main < S) {
-                for (int key = s_main; key < len; ++key) {
-                    const __nv_bfloat16* krow = qkv + ((size_t)row_base + key) * ld + W + h * HD;
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(krow));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(krow + W));
-                }
-                const int nxt = it + gridDim.x;
-                if (nxt < total_items) {
-                    const Item wn = decode_item(nxt, q_blocks, H);
-                    for (int key = s_main; key < S; ++key) {
-                        const __nv_bfloat16* krow = qkv + ((size_t)wn.b * S + key) * ld + W + wn.h * HD;
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(krow));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(krow + W));
-                    }
-                }
-            }
             for (int j = 0; j < nkb; ++j, ++g) {
                 const uint32_t par = g & 1;
                 ptx::mbar_wait(s_full, par);
@@ -547,44 +657,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                 if (lane == 0) ptx::mbar_arrive(p_full);
             }
             // -------------------------------------------------------------- epilogue: (+ tail keys) O / l -> bf16
-            // tail keys: online-softmax update of (m, l) with the scores computed at the top of the item; the per-key
-            // factors are kept so that the output can be finished 32 dims at a time (register budget: 128 per thread)
-            float t_alpha[TAIL_KEYS_MAX], t_p[TAIL_KEYS_MAX];
-#pragma unroll
-            for (int t = 0; t < TAIL_KEYS_MAX; ++t) {
-                t_alpha[t] = 1.f;
-                t_p[t] = 0.f;
-                const int key = s_main + t;
-                if (key < tail_end) {
-                    // s = q . k: all 16 loads in flight at once (q: L2 — the TMA fetched this tile; k: L1, prefetched)
-                    const uint4* qp = reinterpret_cast<const uint4*>(qkv + ((size_t)row_base + qrow) * ld + h * HD);
-                    const uint4* kp = reinterpret_cast<const uint4*>(qkv + ((size_t)row_base + key) * ld + W + h * HD);
-                    uint4 q4[HD / 8], k4[HD / 8];
-#pragma unroll
-                    for (int u = 0; u < HD / 8; ++u) {
-                        q4[u] = __ldg(qp + u);
-                        k4[u] = __ldg(kp + u);
-                    }
-                    float sdot = 0.f;
-#pragma unroll
-                    for (int u = 0; u < HD / 8; ++u) {
-                        const uint32_t kk[4] = {k4[u].x, k4[u].y, k4[u].z, k4[u].w};
-                        const uint32_t qq[4] = {q4[u].x, q4[u].y, q4[u].z, q4[u].w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float2 qa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[e]));
-                            const float2 ka = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk[e]));
-                            sdot = fmaf(qa.x, ka.x, sdot);
-                            sdot = fmaf(qa.y, ka.y, sdot);
-                        }
-                    }
-                    const float sc = sdot * scale_log2e;
+            // remainder key: online-softmax update of (m, l); the output is finished 32 dims at a time below
+            float t_alpha = 1.f, t_p = 0.f;
+            if (has_tail_key) {
+                ptx::mbar_wait(tail_full, nt & 1);
+                if (s_main < tail_end) {
+                    const float sc = sTailS[r];
                     const float m_new = fmaxf(m_run, sc);
-                    t_alpha[t] = ex2(m_run - m_new);
+                    t_alpha = ex2(m_run - m_new);
                     const float pe = ex2(sc - m_new);
                     // the tensor-core path rounds P to bf16 before the PV product: do the same here
-                    t_p[t] = __bfloat162float(__float2bfloat16_rn(pe));
-                    l_run = l_run * t_alpha[t] + pe;
+                    t_p = __bfloat162float(__float2bfloat16_rn(pe));
+                    l_run = l_run * t_alpha + pe;
                     m_run = m_new;
                 }
             }
@@ -607,22 +691,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                     for (int i = 0; i < HD / 2; ++i) o[i] = 0.f;
                 }
                 if (qrow < S) {
+                    if (has_tail_key) {   // o = o * alpha + p * v (alpha = 1, p = 0 for rows the key is masked for)
+                        const uint4* vp = reinterpret_cast<const uint4*>(sTailV) + hf * 4;   // broadcast reads
 #pragma unroll
-                    for (int t = 0; t < TAIL_KEYS_MAX; ++t) {
-                        const int key = s_main + t;
-                        if (key < tail_end) {
-                            const uint4* vp =
-                                reinterpret_cast<const uint4*>(qkv + ((size_t)row_base + key) * ld + 2 * W + h * HD) + hf * 4;
+                        for (int u = 0; u < HD / 16; ++u) {
+                            const uint4 v4 = vp[u];
+                            const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
-                            for (int u = 0; u < HD / 16; ++u) {
-                                const uint4 v4 = __ldg(vp + u);
-                                const uint32_t vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 va = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[e]));
-                                    o[8 * u + 2 * e] = fmaf(o[8 * u + 2 * e], t_alpha[t], t_p[t] * va.x);
-                                    o[8 * u + 2 * e + 1] = fmaf(o[8 * u + 2 * e + 1], t_alpha[t], t_p[t] * va.y);
-                                }
+                            for (int e = 0; e < 4; ++e) {
+                                const float2 va = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&vv[e]));
+                                o[8 * u + 2 * e] = fmaf(o[8 * u + 2 * e], t_alpha, t_p * va.x);
+                                o[8 * u + 2 * e + 1] = fmaf(o[8 * u + 2 * e + 1], t_alpha, t_p * va.y);
                             }
                         }
                     }
@@ -638,6 +717,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                         d4[u] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     }
                 }
+            }
+            if (has_tail_key) {
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tail_empty);
+                ++nt;
             }
             // O has been read: order the tcgen05.ld before the p_full arrival that lets the next item's first PV
             // (accumulate = 0) overwrite it
@@ -673,7 +757,7 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     CUtensorMap tmap = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,
                                     (uint64_t)3 * W * 2, tc::HD, tc::BQ, CU_TENSOR_MAP_SWIZZLE_128B);
     // A short remainder (S = 257, 129, ...) is not worth a 128-wide tile in either dimension.
-    constexpr int TAIL_MAX = 2;   // == the kernel's TAIL_KEYS_MAX
+    constexpr int TAIL_MAX = 1;   // one remainder key / row (S = k * 128 + 1): staged by the kernel's warp 6
     const int rem = S % tc::BQ;
     const bool tail = S >= tc::BQ && rem > 0 && rem <= TAIL_MAX && S <= tc::TAIL_S_MAX;
     const int s_main = tail ? S - rem : S;                       // keys handled by the tensor cores
