@@ -1,4 +1,3 @@
-#include <cstdlib>
 #include "attention.cuh"
 
 namespace mb {
@@ -233,10 +232,6 @@ int launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, in
     // (ViT-B-32: 50 tokens, CLIP text: 77) would leave most of a 128 x 128 tile masked; the 64-row warp-level
     // kernel below wastes far less on them (measured on B200: 0.33 ms vs 0.72 ms per ViT-B-32 step).
     if (S >= 128) {
-        {
-            static const bool use_old = getenv("B200_ATT_OLD") != nullptr;   // TEMPORARY A/B switch
-            if (use_old) return launch_tc4(qkv, out, B, S, W, H, mask, kv_len, stream);
-        }
         return launch_tc(qkv, out, B, S, W, H, mask, kv_len, stream);
     }
     if (W != H * HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);

@@ -17,8 +17,6 @@ int launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, in
            cudaStream_t stream);
 
 // tcgen05 / TMEM implementation (attention_tc.cu)
-int launch_tc4(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
-               cudaStream_t stream);
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
               cudaStream_t stream);
 

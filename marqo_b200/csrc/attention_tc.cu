@@ -10,8 +10,11 @@
 //   O += P_j V_j  (M=128, N=64,  K=128; A = P K-major from smem, B = V MN-major as loaded)  -> TMEM columns [128,192)
 // Warps 2-5: softmax, ONE THREAD PER QUERY ROW (TMEM lane == row): two passes over the row's 128 scores in TMEM
 // (max, then exp2 / sum / bf16 P written to smem in the UMMA K-major swizzled layout), running-max rescale of the O
-// accumulator through tcgen05.ld/st, final 1/l scaling and the bf16 store.  Warp 6: the <= 2 remainder query rows of
-// a sequence such as 257 = 2 * 128 + 1, on the CUDA cores, against the K / V tiles while they sit in shared memory.
+// accumulator through tcgen05.ld/st, final 1/l scaling and the bf16 store.  S of block g + 1 is issued before P.V of
+// block g (also across items), so the next scores are ready when the softmax warps come back.
+// Warp 6: the remainder key and query row of a sequence such as 257 = 2 * 128 + 1 (ViT class token): the key's scores
+// against the 128 rows of the item and its V row are staged in smem for the epilogue; the row runs on mma.sync
+// against the K / V tiles while they sit in shared memory.
 // 113 KB smem + 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's softmax overlaps the other's MMAs.
 #include <algorithm>
 #include <mutex>
@@ -29,16 +32,14 @@ constexpr int BQ = 128;
 constexpr int BKV = 128;
 constexpr int THREADS = 224;   // warp 0 TMA, warp 1 MMA, warps 2-5 softmax, warp 6 remainder rows
 constexpr int KV_STAGES = 2;
-constexpr int TAIL_INLINE_MAX = 1;   // remainder query rows handled inside the main kernel
 constexpr uint32_t Q_BYTES = BQ * HD * 2;        // 16 KB
 constexpr uint32_t KV_TILE_BYTES = BKV * HD * 2;  // 16 KB each for K and V
 constexpr uint32_t P_BYTES = BQ * BKV * 2;        // 32 KB (two 64-key K-major chunks)
-constexpr uint32_t TAILQ_BYTES = TAIL_INLINE_MAX * HD * 2;   // the remainder row's query
 constexpr uint32_t TAILS_BYTES = BQ * 4;                     // the remainder key's score for each of the 128 rows
 constexpr uint32_t TAILV_BYTES = HD * 2;                     // the remainder key's V row
 // 115712 B: two CTAs (+ 1 KB of system-reserved smem each) fill the SM's 228 KB exactly
 constexpr uint32_t SMEM_BYTES =
-    Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES + 128 + TAILQ_BYTES + TAILS_BYTES + TAILV_BYTES + 128;
+    Q_BYTES + KV_STAGES * 2 * KV_TILE_BYTES + P_BYTES + 128 + TAILS_BYTES + TAILV_BYTES;
 static_assert(SMEM_BYTES <= 115712, "two CTAs per SM");
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t S_COL = 0, O_COL = 128;
@@ -66,95 +67,6 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// Query rows that do not fill a 128-row tile (e.g. row 256 of a 257-token ViT sequence): one warp per
-// (batch, head, row).  Phase 1: lanes stride over the keys and compute the scores into shared memory; phase 2: lanes
-// stride over the 64 output dims and accumulate p_j * V[j] with coalesced 128-byte row reads.
-constexpr int TAIL_S_MAX = 1024;
-
-template <int MASK>
-__global__ void __launch_bounds__(128)
-attention_tail_rows_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int S, int W, int H,
-                           int row_lo, const int32_t* __restrict__ kv_len, float scale_log2e, int total) {
-    __shared__ float s_sc[4][TAIL_S_MAX];
-    const int wib = threadIdx.x >> 5;
-    const int wid = blockIdx.x * 4 + wib;
-    const int lane = threadIdx.x & 31;
-    if (wid >= total) return;
-    const int nrows = S - row_lo;
-    const int qrow = row_lo + wid % nrows;
-    const int h = (wid / nrows) % H;
-    const int b = wid / (nrows * H);
-    const size_t ld = (size_t)3 * W;
-    const __nv_bfloat16* seq = qkv + (size_t)b * S * ld;
-    int len = S;
-    if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[b], 0));
-    if (MASK == MASK_CAUSAL) len = min(len, qrow + 1);
-    float* sc = s_sc[wib];
-    // ---- phase 1: scores (log2 domain)
-    float q[HD];
-    {
-        const uint4* qp = reinterpret_cast<const uint4*>(seq + (size_t)qrow * ld + h * HD);
-#pragma unroll
-        for (int u = 0; u < HD / 8; ++u) {
-            const uint4 t4 = __ldg(qp + u);
-            const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
-                q[8 * u + 2 * e] = f2.x * scale_log2e;
-                q[8 * u + 2 * e + 1] = f2.y * scale_log2e;
-            }
-        }
-    }
-    float m = -INFINITY;
-#pragma unroll 2
-    for (int key = lane; key < len; key += 32) {
-        const uint4* kp = reinterpret_cast<const uint4*>(seq + (size_t)key * ld + W + h * HD);
-        uint4 k4[HD / 8];
-#pragma unroll
-        for (int u = 0; u < HD / 8; ++u) k4[u] = __ldg(kp + u);
-        float acc = 0.f;
-#pragma unroll
-        for (int u = 0; u < HD / 8; ++u) {
-            const uint32_t w4[4] = {k4[u].x, k4[u].y, k4[u].z, k4[u].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float2 f2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[e]));
-                acc = fmaf(q[8 * u + 2 * e], f2.x, acc);
-                acc = fmaf(q[8 * u + 2 * e + 1], f2.y, acc);
-            }
-        }
-        sc[key] = acc;
-        m = fmaxf(m, acc);
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    __syncwarp();
-    // ---- softmax numerators (fp32 sum; bf16-rounded P for the PV product, like the tensor-core path)
-    float l = 0.f;
-    for (int key = lane; key < len; key += 32) {
-        const float pe = ex2(sc[key] - m);
-        l += pe;
-        sc[key] = __bfloat162float(__float2bfloat16_rn(pe));
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) l += __shfl_xor_sync(0xffffffffu, l, off);
-    __syncwarp();
-    // ---- phase 2: out[d] = sum_j p_j V[j][d]; lane owns dims 2*lane, 2*lane+1
-    const __nv_bfloat162* vcol = reinterpret_cast<const __nv_bfloat162*>(seq + 2 * W + h * HD) + lane;
-    float ox = 0.f, oy = 0.f;
-#pragma unroll 32
-    for (int key = 0; key < len; ++key) {   // 32 independent 128-byte row reads in flight per warp
-        const float2 v2 = __bfloat1622float2(vcol[(size_t)key * (ld / 2)]);
-        const float pj = sc[key];
-        ox = fmaf(pj, v2.x, ox);
-        oy = fmaf(pj, v2.y, oy);
-    }
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(out + ((size_t)b * S + qrow) * W + h * HD) + lane;
-    *dst = __floats2bfloat162_rn(ox * inv, oy * inv);
 }
 
 // work item -> (batch, head, query block); consecutive items share (batch, head) so the two CTAs that process them
@@ -206,9 +118,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
     uint64_t* tail_full = bars + 10;    // the remainder key's scores + V row are staged (warp 6 -> softmax warps)
     uint64_t* tail_empty = bars + 11;   // ... and have been consumed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-    __nv_bfloat16* sTailQ = reinterpret_cast<__nv_bfloat16*>(sP + P_BYTES + 128);
-    float* sTailS = reinterpret_cast<float*>(sP + P_BYTES + 128 + TAILQ_BYTES);
-    __nv_bfloat16* sTailV = reinterpret_cast<__nv_bfloat16*>(sP + P_BYTES + 128 + TAILQ_BYTES + TAILS_BYTES);
+    float* sTailS = reinterpret_cast<float*>(sP + P_BYTES + 128);
+    __nv_bfloat16* sTailV = reinterpret_cast<__nv_bfloat16*>(sP + P_BYTES + 128 + TAILS_BYTES);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -325,6 +236,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         };
         if (cs.it < total_items) issue_s();
         while (cp.it < total_items) {
+            // S of the NEXT block first (measured: gating this on "inputs already there" loses more overlap than the
+            // occasional wait for the next item's loads costs)
             if (cs.it < total_items) issue_s();
             const int st = gp & 1;
             ptx::mbar_wait(p_full, gp & 1);  // P of this block is in smem and O has been rescaled
@@ -756,17 +669,14 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     // rows past the end of the matrix are zero-filled, rows of the next sequence are masked by key index
     CUtensorMap tmap = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,
                                     (uint64_t)3 * W * 2, tc::HD, tc::BQ, CU_TENSOR_MAP_SWIZZLE_128B);
-    // A short remainder (S = 257, 129, ...) is not worth a 128-wide tile in either dimension.
-    constexpr int TAIL_MAX = 1;   // one remainder key / row (S = k * 128 + 1): staged by the kernel's warp 6
+    // A remainder of ONE token (S = 257, 129, ...: a class token on top of a power-of-two grid) is not worth a 128-wide
+    // tile in either dimension: warp 6 of the kernel handles that key and that query row.
     const int rem = S % tc::BQ;
-    const bool tail = S >= tc::BQ && rem > 0 && rem <= TAIL_MAX && S <= tc::TAIL_S_MAX;
+    const bool tail = S > tc::BQ && rem == 1;
     const int s_main = tail ? S - rem : S;                       // keys handled by the tensor cores
     const int q_blocks = tail ? S / tc::BQ : (S + tc::BQ - 1) / tc::BQ;
     const float scale_log2e = 0.125f * 1.4426950408889634f;
-    // remainder query rows inside the main kernel when every key block fits the 2-stage ring without reuse
-    const bool inline_tail = tail && rem <= tc::TAIL_INLINE_MAX;
-    const int inline_rows = inline_tail ? rem : 0;
-    const int tail_total = (tail && !inline_tail) ? B * H * rem : 0;
+    const int inline_rows = tail ? rem : 0;
     // persistent grid: two CTAs per SM; an odd CTA count when q_blocks is even makes every CTA alternate between the
     // query blocks of a sequence, so the remainder-row work of the last block is spread over all CTAs
     const int total_items = B * H * q_blocks;
@@ -775,28 +685,26 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     int grid = 2 * sm_count(device);
     if ((q_blocks & 1) == 0 && (grid & 1) == 0) grid -= 1;
     grid = std::min(grid, total_items);
-    auto run = [&](auto kern, auto tail_kern) {
+    auto run = [&](auto kern) {
         kern<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, H, kv_len, scale_log2e, s_main, inline_rows,
                                                           q_blocks, total_items);
-        if (tail_total > 0)
-            tail_kern<<<(tail_total + 3) / 4, 128, 0, stream>>>(qkv, out, S, W, H, s_main, kv_len, scale_log2e, tail_total);
     };
     switch (mask) {
         case MASK_NONE:
-            run(tc::attention_tc_kernel<MASK_NONE>, tc::attention_tail_rows_kernel<MASK_NONE>);
+            run(tc::attention_tc_kernel<MASK_NONE>);
             break;
         case MASK_CAUSAL:
-            run(tc::attention_tc_kernel<MASK_CAUSAL>, tc::attention_tail_rows_kernel<MASK_CAUSAL>);
+            run(tc::attention_tc_kernel<MASK_CAUSAL>);
             break;
         case MASK_KEYLEN:
             if (!kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
-            run(tc::attention_tc_kernel<MASK_KEYLEN>, tc::attention_tail_rows_kernel<MASK_KEYLEN>);
+            run(tc::attention_tc_kernel<MASK_KEYLEN>);
             break;
         default:
             fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);
     }
     MB_CUDA(cudaGetLastError());
-    return tail_total > 0 ? 2 : 1;
+    return 1;
 }
 
 }  // namespace attention
