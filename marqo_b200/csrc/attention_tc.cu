@@ -236,9 +236,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         };
         if (cs.it < total_items) issue_s();
         while (cp.it < total_items) {
-            // S of the NEXT block first (measured: gating this on "inputs already there" loses more overlap than the
-            // occasional wait for the next item's loads costs)
-            if (cs.it < total_items) issue_s();
+            // S of the NEXT block first: the tensor core computes it while the softmax warps are still busy with this
+            // block's P, so they go straight from P_g to S_{g+1} and need P.V_g only one pass later — also across an
+            // item boundary (252 vs 288 us per ViT-L layer).  Only single-block items (S = 128) prefer their P.V first:
+            // there every block ends an item and the epilogue is waiting for it (56 vs 62 us).  Gating the early S on
+            // "inputs already there" was slower in both cases.
+            const bool s_first = cs.it < total_items && (cs.j != 0 || cp.nkb > 1);
+            if (s_first) issue_s();
             const int st = gp & 1;
             ptx::mbar_wait(p_full, gp & 1);  // P of this block is in smem and O has been rescaled
             ptx::tc_fence_after();
@@ -258,6 +262,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
             __syncwarp();
             ++gp;
             advance(cp, false);
+            if (!s_first && cs.it < total_items) issue_s();
         }
     } else if (warp == 6) {
         // ================================================================== remainder key + remainder query row
