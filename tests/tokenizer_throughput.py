@@ -1,4 +1,4 @@
-"""Dev probe (host only): texts/s of the C++ tokenizers vs the checkers (HF `tokenizers` for WordPiece, the Python
+"""Checker-side throughput comparison, kept under tests/ because it runs the oracle tokenizers (host only): texts/s of the C++ tokenizers vs the checkers (HF `tokenizers` for WordPiece, the Python
 restatement of open_clip's SimpleTokenizer for CLIP BPE) on synthetic English-like text.  Not a bench line."""
 import json
 import sys
