@@ -15,7 +15,9 @@
 //   patches   bf16 [images * grid^2, kpad]  normalised im2col of the uint8 input (ToTensor + Normalize fused)
 // Every Linear is the tcgen05 GEMM of gemm.cu with bias / activation / residual-add fused into its epilogue.
 #include <algorithm>
+#include <cstdlib>
 #include <map>
+#include <tuple>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -85,6 +87,20 @@ struct b200_model {
     std::vector<cudaEvent_t> prof_ev;  // pairs
     std::vector<int> prof_cls;         // 0 = gemm, 1 = attention
     int prof_n = 0;
+    // CUDA graphs of small (launch-bound) forward passes, keyed by everything the captured launches depend on
+    struct GraphKey {
+        int kind, n, S, normalize;
+        const void *in0, *in1, *out;
+        bool operator<(const GraphKey& o) const {
+            return std::tie(kind, n, S, normalize, in0, in1, out) < std::tie(o.kind, o.n, o.S, o.normalize, o.in0, o.in1, o.out);
+        }
+    };
+    struct GraphEntry {
+        cudaGraphExec_t exec = nullptr;   // null: seen once (ran eagerly), captured on the next use
+        int launches = 0;
+    };
+    std::map<GraphKey, GraphEntry> graphs;
+    bool external_stream = false;
     std::mutex mu;
 };
 
@@ -118,6 +134,8 @@ void model_free(b200_model* m) {
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     for (cudaEvent_t e : m->prof_ev) cudaEventDestroy(e);
+    for (auto& kv : m->graphs)
+        if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
     delete m;
 }
@@ -333,7 +351,8 @@ void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
 }
 
 // images already as device uint8 [n, S, S, 3] (u8 != nullptr) or device fp32 CHW (f32 != nullptr)
-void forward_images(b200_model* m, Counter& c, const uint8_t* u8, const float* f32, int n, int normalize, float* d_out) {
+void forward_images_eager(b200_model* m, Counter& c, const uint8_t* u8, const float* f32, int n, int normalize,
+                          float* d_out) {
     const TowerW& T = m->vision;
     const int S = T.d.image_size, p = T.d.patch, w = T.d.width, G = T.grid * T.grid;
     if (u8)
@@ -356,8 +375,8 @@ void forward_images(b200_model* m, Counter& c, const uint8_t* u8, const float* f
     c.n += 3;
 }
 
-void forward_tokens(b200_model* m, Counter& c, const int32_t* d_ids, const int32_t* d_mask, int n, int S, int normalize,
-                    float* d_out) {
+void forward_tokens_eager(b200_model* m, Counter& c, const int32_t* d_ids, const int32_t* d_mask, int n, int S,
+                          int normalize, float* d_out) {
     const TowerW& T = m->text;
     const int w = T.d.width;
     if (m->desc.arch == B200_ARCH_CLIP) {
@@ -377,6 +396,49 @@ void forward_tokens(b200_model* m, Counter& c, const int32_t* d_ids, const int32
     }
 }
 
+// Small batches (a single query, a handful of chunks) are launch-bound: ~90-180 kernels of a few microseconds each,
+// every GEMM launch also encoding two tensor maps on the host.  The first call of a shape runs eagerly (one-time
+// attribute set-up happens there), the second is captured into a CUDA graph, later ones replay it.
+constexpr long long GRAPH_MAX_TOKENS = 8192;
+constexpr size_t GRAPH_MAX_ENTRIES = 64;
+
+template <class Body>
+void run_graphed(b200_model* m, Counter& c, const b200_model::GraphKey& key, long long tokens, Body&& body) {
+    static const bool disabled = getenv("MARQO_B200_NO_GRAPHS") != nullptr;   // kill switch / A-B timing
+    if (disabled || tokens > GRAPH_MAX_TOKENS || m->profiling || m->external_stream) {
+        body(c);
+        return;
+    }
+    auto it = m->graphs.find(key);
+    if (it == m->graphs.end()) {
+        if (m->graphs.size() < GRAPH_MAX_ENTRIES) m->graphs[key] = b200_model::GraphEntry{};
+        body(c);
+        return;
+    }
+    if (!it->second.exec) {
+        Counter cc;
+        MB_CUDA(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+        cudaGraph_t graph = nullptr;
+        try {
+            body(cc);
+        } catch (...) {
+            cudaStreamEndCapture(m->stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            m->graphs.erase(it);
+            throw;
+        }
+        MB_CUDA(cudaStreamEndCapture(m->stream, &graph));
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        MB_CUDA(e);
+        it->second.exec = exec;
+        it->second.launches = cc.n;
+    }
+    MB_CUDA(cudaGraphLaunch(it->second.exec, m->stream));
+    c.n += it->second.launches;
+}
+
 void ensure_in_dev(b200_model* m, size_t bytes) {
     if (bytes <= m->in_dev_bytes) return;
     cudaFree(m->in_dev);
@@ -384,6 +446,19 @@ void ensure_in_dev(b200_model* m, size_t bytes) {
     m->in_dev_bytes = 0;
     dev_alloc(&m->in_dev, bytes);
     m->in_dev_bytes = bytes;
+}
+
+void forward_images(b200_model* m, Counter& c, const uint8_t* u8, const float* f32, int n, int normalize, float* d_out) {
+    const b200_model::GraphKey key{0, n, 0, normalize, u8, f32, d_out};
+    run_graphed(m, c, key, (long long)n * m->vision.tokens,
+                [&](Counter& cc) { forward_images_eager(m, cc, u8, f32, n, normalize, d_out); });
+}
+
+void forward_tokens(b200_model* m, Counter& c, const int32_t* d_ids, const int32_t* d_mask, int n, int S, int normalize,
+                    float* d_out) {
+    const b200_model::GraphKey key{1, n, S, normalize, d_ids, d_mask, d_out};
+    run_graphed(m, c, key, (long long)n * S,
+                [&](Counter& cc) { forward_tokens_eager(m, cc, d_ids, d_mask, n, S, normalize, d_out); });
 }
 
 void require_ready(b200_model* m) {
@@ -732,6 +807,7 @@ int b200_model_set_stream(b200_model* m, void* cuda_stream, int use_external) {
         DeviceGuard g(m->device);
         MB_CUDA(cudaStreamSynchronize(m->stream));
         m->stream = use_external ? reinterpret_cast<cudaStream_t>(cuda_stream) : m->own_stream;
+        m->external_stream = use_external != 0;   // a caller's stream may itself be under capture: no graphs there
     });
 }
 

@@ -86,6 +86,38 @@ def test_tiny_bert(gpu_required, pool):
     _check(enc.encode_tokens(ids.numpy()), E.bert_encode(sd, cfg, ids, None))
 
 
+def test_repeated_small_calls_replay_cuda_graphs(gpu_required):
+    """Small calls of one shape: 1st eager, 2nd captured into a CUDA graph, later ones replayed — with NEW inputs each
+    time (the graph must read the staging buffers, not bake values in), interleaved with other shapes and towers."""
+    from marqo_b200.engine import Encoder
+    cfg = E.tiny_clip("gelu")
+    sd = E.make_clip_weights(cfg, seed=13)
+    enc = Encoder("clip", _clip_config(cfg), sd, max_batch=8)
+    g = torch.Generator().manual_seed(5)
+    rng = np.random.default_rng(5)
+    launches = []
+    for it in range(5):
+        ids = _text_ids(g, 3, cfg.text.ctx, cfg.text.vocab)
+        _check(enc.encode_tokens(ids.numpy()), E.clip_encode_text(sd, cfg, ids))
+        launches.append(enc.last_timing()[1])
+        img = rng.integers(0, 256, size=(2, 224, 224, 3), dtype=np.uint8)
+        _check(enc.encode_images_u8(img), E.clip_encode_image(sd, cfg, E.clip_preprocess_u8(img)))
+        if it == 2:   # another shape in between does not disturb the cached graphs
+            ids1 = _text_ids(g, 1, cfg.text.ctx, cfg.text.vocab)
+            _check(enc.encode_tokens(ids1.numpy()), E.clip_encode_text(sd, cfg, ids1))
+        _check(enc.encode_tokens(ids.numpy(), normalize=False), E.clip_encode_text(sd, cfg, ids, normalize=False), norm=False)
+    assert len(set(launches)) == 1          # the kernel count reported for a replayed graph is the eager one
+    bcfg = E.tiny_bert("mean")
+    bsd = E.make_bert_weights(bcfg, seed=14)
+    benc = Encoder("bert", _bert_config(bcfg), bsd, max_batch=16)
+    for it in range(4):
+        ids = torch.randint(1, bcfg.vocab, (4, 24), generator=g)
+        mask = torch.ones(4, 24, dtype=torch.int64)
+        L = int(torch.randint(1, 25, (1,), generator=g))
+        mask[1, L:] = 0                       # the key-length mask changes between replays
+        _check(benc.encode_tokens(ids.numpy(), mask.numpy()), E.bert_encode(bsd, bcfg, ids, mask))
+
+
 def test_vit_b_32(gpu_required):
     """BASELINE.json configs[1] architecture (open_clip/ViT-B-32), seeded weights, batch 8."""
     from marqo_b200.engine import Encoder
