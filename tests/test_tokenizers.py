@@ -223,3 +223,21 @@ def test_clip_oracle_agrees_with_hf_cliptokenizer(clip, tmp_path):
         want = hf(t)["input_ids"]
         assert [ref.sot] + ref.encode(t) + [ref.eot] == want
         assert mine([t])[0, :len(want)].tolist() == want
+
+
+def test_tokenizer_handles_are_thread_safe(wp, clip):
+    """Marqo calls vectorise from up to 16 request threads with no lock: one immutable handle, many callers."""
+    from concurrent.futures import ThreadPoolExecutor
+    mine_wp, ref_wp, OT = wp
+    mine_bpe, ref_bpe, _ = clip
+    texts = [f"hello world {i} the quick brown fox's photo #{i} café" for i in range(64)]
+    want_wp = mine_wp(texts, max_length=32)["input_ids"]
+    want_bpe = mine_bpe(texts)
+
+    def work(_):
+        a = mine_wp(texts, max_length=32)["input_ids"]
+        b = mine_bpe(texts)
+        return np.array_equal(a, want_wp) and np.array_equal(b, want_bpe)
+
+    with ThreadPoolExecutor(8) as pool:
+        assert all(pool.map(work, range(32)))
