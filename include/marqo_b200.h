@@ -49,6 +49,12 @@ const char* b200_last_error(void);
 /* Number of visible CUDA devices with compute capability 10.x. */
 int b200_device_count(int* out_count);
 
+/* Page-locked host memory (cudaHostAlloc, portable) for staging inputs: host-to-device copies from it run at the full
+ * PCIe rate.  The reference stages every image separately (`.to(device)` per image at
+ * src/marqo/tensor_search/add_docs.py:129-134); the adapters assemble a batch in one such buffer instead. */
+int b200_host_alloc(size_t bytes, void** out);
+int b200_host_free(void* p);
+
 /* ===================================================================================== */
 /* Score + top-k over a GPU-resident embedding matrix  (replaces the Vespa   */
 /* nearestNeighbor / closeness / top-k round trip specified by                            */

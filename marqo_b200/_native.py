@@ -50,6 +50,8 @@ _SIGNATURES = {
     "b200_abi_version": (C.c_int, []),
     "b200_last_error": (C.c_char_p, []),
     "b200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "b200_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
+    "b200_host_free": (C.c_int, [_P]),
     "b200_index_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(_P)]),
     "b200_index_destroy": (C.c_int, [_P]),
     "b200_index_add": (C.c_int, [_P, _P, _P, C.c_int64]),

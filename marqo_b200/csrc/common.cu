@@ -80,6 +80,32 @@ int b200_device_count(int* out_count) {
     });
 }
 
+int b200_host_alloc(size_t bytes, void** out) {
+    return mb::guarded([&] {
+        MB_CHECK_ARG(out != nullptr, "out is NULL");
+        *out = nullptr;
+        MB_CHECK_ARG(bytes > 0, "bytes must be positive");
+        void* p = nullptr;
+        const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+        if (e == cudaErrorMemoryAllocation) {
+            cudaGetLastError();
+            mb::fail(B200_ERR_OOM, "cudaHostAlloc(%zu bytes) failed: out of page-locked host memory", bytes);
+        }
+        if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) {
+            cudaGetLastError();
+            mb::fail(B200_ERR_NO_DEVICE, "no CUDA device available (marqo_b200 has no CPU fallback)");
+        }
+        MB_CUDA(e);
+        *out = p;
+    });
+}
+
+int b200_host_free(void* p) {
+    return mb::guarded([&] {
+        if (p) MB_CUDA(cudaFreeHost(p));
+    });
+}
+
 int b200_fuse_vectors(const double* vecs, const double* weights, int n, int dim, int normalize, double* out) {
     return mb::guarded([&] {
         MB_CHECK_ARG(vecs && weights && out, "NULL argument");

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -240,6 +241,9 @@ class Encoder:
         else:
             raise ValueError(f"unknown arch {arch!r}")
         self.embed_dim = int(d.embed_dim)
+        self._stage_ptr, self._stage_bytes = None, 0
+        self._stage_lock = threading.Lock()
+        self._pool = None
         h = C.c_void_p()
         N.check(self._lib.b200_model_create(self.device, C.byref(d), C.byref(h)))
         self._h = h
@@ -256,6 +260,13 @@ class Encoder:
         h, self._h = getattr(self, "_h", None), None
         if h:
             self._lib.b200_model_destroy(h)
+        pool, self._pool = getattr(self, "_pool", None), None
+        if pool is not None:
+            pool.shutdown(wait=False)
+        st, self._stage_ptr = getattr(self, "_stage_ptr", None), None
+        if st:
+            self._lib.b200_host_free(st)
+            self._stage_bytes = 0
 
     def __del__(self):
         try:
@@ -267,6 +278,48 @@ class Encoder:
         if not self._h:
             raise RuntimeError("Encoder is closed")
         return self._h
+
+    def _staging(self, nbytes: int) -> np.ndarray:
+        """A reusable page-locked uint8 buffer of at least nbytes (caller holds self._stage_lock)."""
+        if getattr(self, "_stage_bytes", 0) < nbytes:
+            if getattr(self, "_stage_ptr", None):
+                self._lib.b200_host_free(self._stage_ptr)
+                self._stage_ptr, self._stage_bytes = None, 0
+            want = int(nbytes * 1.25) + 4096
+            p = C.c_void_p()
+            N.check(self._lib.b200_host_alloc(want, C.byref(p)))
+            self._stage_ptr, self._stage_bytes = p, want
+        return np.ctypeslib.as_array((C.c_uint8 * self._stage_bytes).from_address(self._stage_ptr.value))
+
+    def encode_images_u8_list(self, images: Sequence[np.ndarray], normalize: bool = True) -> np.ndarray:
+        """uint8 HWC images of ONE size, given one by one (what Marqo's download threads hand over): they are
+        assembled in a reusable page-locked staging buffer — no fresh 38 MB allocation per batch, full-rate H2D."""
+        n = len(images)
+        if n == 0:
+            raise ValueError("expected at least one image")
+        h, w = images[0].shape[:2]
+        out = np.empty((n, self.embed_dim), np.float32)
+        with self._stage_lock:
+            buf = self._staging(n * h * w * 3)[: n * h * w * 3].reshape(n, h, w, 3)
+            for i, a in enumerate(images):
+                if a.shape != (h, w, 3) or a.dtype != np.uint8:
+                    raise ValueError(f"image {i}: expected uint8 [{h}, {w}, 3], got {a.dtype} {a.shape}")
+
+            def fill(lo: int, hi: int) -> None:
+                for i in range(lo, hi):
+                    np.copyto(buf[i], images[i])   # releases the GIL for the memcpy
+
+            if n * h * w * 3 >= (8 << 20):   # a 38 MB batch: ~4 ms on one core, < 1 ms on eight
+                if self._pool is None:
+                    from concurrent.futures import ThreadPoolExecutor
+                    self._pool = ThreadPoolExecutor(8, thread_name_prefix="b200-stage")
+                step = (n + 7) // 8
+                list(self._pool.map(lambda lo: fill(lo, min(n, lo + step)), range(0, n, step)))
+            else:
+                fill(0, n)
+            N.check(self._lib.b200_model_encode_images_u8(self._handle(), C.c_void_p(self._stage_ptr.value), n, h, w,
+                                                          1 if normalize else 0, _ptr(out)))
+        return out
 
     def encode_images_u8(self, hwc: np.ndarray, normalize: bool = True) -> np.ndarray:
         a = _as(hwc, np.uint8)

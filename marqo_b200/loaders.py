@@ -149,7 +149,7 @@ class B200OpenCLIP:
         for i, a in enumerate(u8):
             groups.setdefault(a.shape[:2], []).append(i)
         for (h, w), idx in groups.items():
-            out[idx] = self.model.encode_images_u8(np.stack([u8[i] for i in idx]), normalize=bool(normalize))
+            out[idx] = self.model.encode_images_u8_list([u8[i] for i in idx], normalize=bool(normalize))
         return out
 
     def encode_text(self, sentence: Union[str, List[str]], normalize=True) -> np.ndarray:
