@@ -241,3 +241,24 @@ def test_tokenizer_handles_are_thread_safe(wp, clip):
 
     with ThreadPoolExecutor(8) as pool:
         assert all(pool.map(work, range(32)))
+
+
+def test_property_random_unicode_text(wp, clip):
+    """hypothesis: arbitrary Unicode strings (any plane, any category, surrogates excluded) tokenise identically."""
+    from hypothesis import given, settings, strategies as st
+    mine_wp, ref_wp, OT = wp
+    mine_bpe, ref_bpe, _ = clip
+    piece = st.one_of(st.characters(blacklist_categories=("Cs",)),
+                      st.sampled_from(list(" \t\n.,!?'&#;[]<>_-") + ["[SEP]", "[MASK]", "&amp;", "&#x41;", "'s", "Σ"]))
+    text = st.lists(piece, max_size=40).map("".join)
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.lists(text, min_size=1, max_size=6))
+    def check(texts):
+        got = mine_wp(texts, max_length=24)
+        ids, mask = OT.bert_encode_batch(ref_wp, texts, 24)
+        np.testing.assert_array_equal(got["input_ids"], ids)
+        np.testing.assert_array_equal(got["attention_mask"], mask)
+        np.testing.assert_array_equal(mine_bpe(texts, context_length=20), ref_bpe(texts, context_length=20))
+
+    check()
