@@ -4,9 +4,10 @@ Drop-in for `Config.vespa_client` (src/marqo/config.py:35) on the dense path: `f
 `delete_batch` keep the argument meaning and the response shapes of src/marqo/vespa/vespa_client.py:198-242,
 :267-296, :405-440, :468-500 and src/marqo/vespa/models/{query_result,feed_response,get_document_response,
 delete_document_response}.py.  Tensor queries (ranking == 'embedding_similarity', YQL made only of
-`nearestNeighbor(...)` terms) are answered from the GPU-resident fp16 matrix by the exact score + top-k kernels;
-everything else (bm25, hybrid, filters) is handed to the optional `delegate` — a real VespaClient — or rejected with
-VespaError ("delegate ... rather than answer").
+`nearestNeighbor(...)` terms, optionally followed by the ` AND <filter>` text of unstructured / semi-structured indexes) are
+answered from the GPU-resident fp16 matrix by the exact score + top-k kernels; everything else (bm25, hybrid, filters in
+another grammar) is handed to the optional `delegate` — a real VespaClient — or rejected with VespaError (SURVEY §8b:
+"delegate ... rather than answer").
 
 Semantics implemented (from the schema generators the reference ships, executed inside Vespa today):
   score(doc) = max over searched tensor fields, max over chunks, of closeness(q, chunk)
@@ -28,6 +29,7 @@ import numpy as np
 
 from ._native import ERR_UNSUPPORTED, NativeError
 from .engine import RowStore
+from .yql_filter import FilterSyntaxError, compile_filter
 from .errors import VespaError, VespaStatusError
 
 RANK_PROFILE_EMBEDDING_SIMILARITY = "embedding_similarity"   # */common.py
@@ -230,16 +232,34 @@ class GpuTensorIndex:
         return _wrap("FeedBatchResponse", {"responses": responses, "errors": errors})
 
     # ------------------------------------------------------------------------------------------------ query
+    @staticmethod
+    def _split_where(yql: str) -> Tuple[bool, Optional[str]]:
+        """-> (the where clause is nearestNeighbor terms [AND <filter>], filter text or None).
+        unstructured_vespa_index.py:59-66: `where {tensor_term}{' AND ' + filter}`; structured_vespa_index.py:645-688 ORs
+        one nearestNeighbor term per searched field inside parentheses."""
+        m = _WHERE.search(yql or "")
+        if not m:
+            return False, None
+        rest = _NN_TERM.sub("", m.group(1))
+        head, sep, tail = rest.partition(" AND ")
+        if re.sub(r"\bOR\b|[()\s;]", "", head):
+            return False, None
+        if not sep:
+            return True, None
+        text = tail.strip().rstrip(";").strip()
+        return (True, text) if text else (False, None)
+
     def _is_tensor_query(self, yql: str, ranking: Optional[str], query_features: Optional[dict]) -> bool:
         if ranking not in (RANK_PROFILE_EMBEDDING_SIMILARITY, RANK_PROFILE_EMBEDDING_SIMILARITY_MODIFIERS_2_9):
             return False
-        m = _WHERE.search(yql or "")
-        if not m:
+        ok, filter_text = self._split_where(yql)
+        if not ok:
             return False
-        rest = _NN_TERM.sub("", m.group(1))
-        rest = re.sub(r"\bOR\b|[()\s;]", "", rest)
-        if rest:           # an `AND <filter>` suffix (unstructured_vespa_index.py:62-66) or anything else
-            return False
+        if filter_text is not None:
+            try:
+                compile_filter(filter_text)
+            except FilterSyntaxError:     # e.g. a structured index's filter grammar: not ours to answer
+                return False
         qf = query_features or {}
         if not any(k in qf for k in QUERY_INPUT_EMBEDDINGS):
             return False
@@ -275,13 +295,15 @@ class GpuTensorIndex:
             mult.update(self._weights(query_features.get(k)))
         for k in ADD_WEIGHTS_INPUTS:
             add.update(self._weights(query_features.get(k)))
+        filter_text = self._split_where(yql)[1]
+        keep = compile_filter(filter_text) if filter_text is not None else None
         with self._lock:
             s = self._schemas.get(schema)
             children, n_docs = [], 0
             if s is not None:
                 n_docs = sum(1 for d in s.doc_ids if d is not None)
                 try:
-                    children = self._search(s, schema, fields, q, hits, offset, mult, add)
+                    children = self._search(s, schema, fields, q, hits, offset, mult, add, keep)
                 except NativeError as e:
                     if e.code != ERR_UNSUPPORTED:
                         raise
@@ -323,8 +345,11 @@ class GpuTensorIndex:
                 a += w * attrs[name]
         return m, a
 
+    MAX_FETCH = 10000   # b200_index_search's own k limit (Marqo's limit + offset cap, tensor_search.py:1568-1588)
+
     def _search(self, s: _Schema, schema: str, fields: List[str], q: np.ndarray, hits: int, offset: int,
-                mult: Optional[Dict[str, float]] = None, add: Optional[Dict[str, float]] = None) -> List[dict]:
+                mult: Optional[Dict[str, float]] = None, add: Optional[Dict[str, float]] = None,
+                keep=None) -> List[dict]:
         k = hits + offset
         if k <= 0:
             return []
@@ -332,6 +357,13 @@ class GpuTensorIndex:
         mult_cols = [(s.attr_col[n], w) for n, w in (mult or {}).items() if n in s.attr_col]
         add_cols = [(s.attr_col[n], w) for n, w in (add or {}).items() if n in s.attr_col]
         modified = bool(mult_cols) or bool(add_cols)
+        verdict: Dict[int, bool] = {}
+
+        def allowed(num: int) -> bool:
+            if num not in verdict:
+                verdict[num] = bool(keep(s.fields[num] or {}))
+            return verdict[num]
+
         best: Dict[int, Tuple[float, str, int]] = {}   # doc number -> (score, field, row)
         for f in fields:
             store = s.stores.get(f)
@@ -340,16 +372,29 @@ class GpuTensorIndex:
             if q.shape[-1] != store.dim:
                 raise VespaStatusError(400, f"Expected a tensor of dimension {store.dim} for query input but got "
                                             f"{q.shape[-1]}")
-            if modified:
-                doc, row, score = store.search_modified(q[None, :], k, mult_cols, add_cols)
-            else:
-                doc, row, score = store.search(q[None, :], k)
-            for d, r, sc in zip(doc[0], row[0], score[0]):
-                if d < 0:
-                    continue
-                cur = best.get(int(d))
+            # A filter is evaluated on the host against the stored fields; the exact top-k of the ALLOWED documents is
+            # the first k allowed entries of the unfiltered ranking, so fetch deeper until k of them have been seen.
+            fetch = k
+            while True:
+                if modified:
+                    doc, row, score = store.search_modified(q[None, :], fetch, mult_cols, add_cols)
+                else:
+                    doc, row, score = store.search(q[None, :], fetch)
+                found = [(int(d), int(r), float(sc)) for d, r, sc in zip(doc[0], row[0], score[0]) if d >= 0]
+                if keep is not None:
+                    kept = [h for h in found if allowed(h[0])]
+                    exhausted = len(found) < fetch
+                    if len(kept) < k and not exhausted:
+                        if fetch >= self.MAX_FETCH:
+                            raise NativeError(ERR_UNSUPPORTED, f"filter leaves fewer than {k} of the best {fetch} documents")
+                        fetch = min(self.MAX_FETCH, fetch * 4)
+                        continue
+                    found = kept[:k]
+                break
+            for d, r, sc in found:
+                cur = best.get(d)
                 if cur is None or sc > cur[0]:
-                    best[int(d)] = (float(sc), f, int(r))
+                    best[d] = (sc, f, r)
         ranked = sorted(best.items(), key=lambda kv: (-kv[1][0], kv[0]))[offset:offset + hits]
         children = []
         for num, (sc, f, r) in ranked:

@@ -339,6 +339,13 @@ def test_gpu_tensor_index_snapshot_restart(gpu_required, tmp_path):
     again.close()
 
 
+def test_gpu_tensor_index_filtered_search(gpu_required):
+    """Tensor search with a filter (tensor_search.py -> unstructured_vespa_index.py:59-66,135-226): exact top-k among
+    the documents the filter keeps; scenario shared with the CPU stand-in run (tests/_filter_scenario.py)."""
+    from _filter_scenario import run_filtered_search_scenario
+    run_filtered_search_scenario()
+
+
 def test_concurrent_encode_calls_are_serialised_per_handle(gpu_required):
     """Marqo calls encode() from up to 16 request threads with no lock; the handle serialises internally."""
     import threading

@@ -1,0 +1,181 @@
+"""Filtered tensor search, host side (no GPU): the YQL filter text comes from THE REFERENCE's own generator
+(tests/golden/make_filter_golden.py -> filter_golden.json); marqo_b200.yql_filter must accept every one of them and select
+the documents Vespa would, given the schema the reference deploys (whole-value, case-insensitive attribute matching;
+sameElement on one map entry)."""
+import json
+from pathlib import Path
+
+import pytest
+
+GOLD = json.loads((Path(__file__).resolve().parent / "golden" / "filter_golden.json").read_text())
+
+
+def _vespa_fields(doc_id, logical):
+    """Logical Marqo document -> the stored Vespa fields of an unstructured index (unstructured_document.py:95-125)."""
+    f = {"marqo__id": doc_id, "marqo__short_string_fields": {}, "marqo__string_array": [], "marqo__int_fields": {},
+         "marqo__float_fields": {}, "marqo__bool_fields": {}}
+    for k, v in logical.items():
+        if isinstance(v, bool):
+            f["marqo__bool_fields"][k] = int(v)
+        elif isinstance(v, str):
+            f["marqo__short_string_fields"][k] = v
+        elif isinstance(v, list):
+            f["marqo__string_array"].extend(f"{k}::{e}" for e in v)
+        elif isinstance(v, int):
+            f["marqo__int_fields"][k] = v
+        elif isinstance(v, float):
+            f["marqo__float_fields"][k] = v
+    return f
+
+
+DOCS = {
+    "d0": dict(color="red", price=15, in_stock=True, tags=["sale", "new"], year=2024, rating=4.5, title='say "hi"',
+               a=1, b=2, c=3, d=4, **{"meta.size": "large"}),
+    "d1": dict(color="blue", price=25, in_stock=False, tags=["new"], year=2023, rating=3.0, a=1, b=5, c=3, d=5),
+    "d2": dict(color="dark red", price=10.5, in_stock=True, year=2024, rating=4.5, a=2),
+    "d3": dict(color="Red", price=3, in_stock="true", tags=["sale"]),
+    "doc7": dict(),
+}
+EXPECTED = {
+    "color:red": {"d0", "d3"},
+    "color:(dark red)": {"d2"},
+    "price:[10 TO 20]": {"d0", "d2"},
+    "price:[10.5 TO *]": {"d0", "d1", "d2"},
+    "price:[* TO 3]": {"d3"},
+    "in_stock:true": {"d0", "d2", "d3"},
+    "in_stock:false AND color:red": set(),
+    "color:red OR color:blue": {"d0", "d1", "d3"},
+    "NOT color:red": {"d1", "d2", "doc7"},
+    "(color:red OR color:blue) AND price:[0 TO 100]": {"d0", "d1", "d3"},
+    "NOT (color:red AND in_stock:true)": {"d1", "d2", "doc7"},
+    "tags:sale": {"d0", "d3"},
+    "year:2024": {"d0", "d2"},
+    "rating:4.5": {"d0", "d2"},
+    "_id:doc7": {"doc7"},
+    "meta.size:large": {"d0"},
+    'title:(say \\"hi\\")': {"d0"},
+    "a:1 AND (b:2 OR (c:3 AND NOT d:4))": {"d0", "d1"},
+    "color:RED": {"d0", "d3"},
+}
+
+
+def test_every_reference_filter_is_accepted_and_selects_the_right_documents():
+    from marqo_b200.yql_filter import compile_filter
+    assert {g["filter"] for g in GOLD} == set(EXPECTED)
+    stored = {doc_id: _vespa_fields(doc_id, logical) for doc_id, logical in DOCS.items()}
+    for g in GOLD:
+        pred = compile_filter(g["yql"])
+        got = {doc_id for doc_id, fields in stored.items() if pred(fields)}
+        assert got == EXPECTED[g["filter"]], (g["filter"], g["yql"], got)
+
+
+@pytest.mark.parametrize("bad", [
+    "price > 3",                                             # a structured-index filter: other grammar -> delegate
+    '(title contains "x") AND',
+    '((a contains "x") AND (b contains "y") OR (c contains "z"))',
+    '(marqo__int_fields contains sameElement(key contains "p"))',
+    '(x contains "unterminated)',
+])
+def test_other_grammars_are_rejected(bad):
+    from marqo_b200.yql_filter import FilterSyntaxError, compile_filter
+    with pytest.raises(FilterSyntaxError):
+        compile_filter(bad)
+
+
+def _nn(field="marqo__embeddings", k=10):
+    return (f"({{targetHits:{k}, approximate:False, hnsw.exploreAdditionalHits:0}}"
+            f"nearestNeighbor({field}, marqo__query_embedding))")
+
+
+def test_adapter_recognises_filtered_tensor_queries():
+    """unstructured_vespa_index.py:59-66 appends ' AND <filter>' to the nearestNeighbor term; the adapter answers those
+    (and only those) whose filter text is in the grammar above."""
+    from marqo_b200.gpu_tensor_index import GpuTensorIndex
+    ix = GpuTensorIndex.__new__(GpuTensorIndex)          # classification is pure host logic: no device needed
+    qf = {"marqo__query_embedding": [0.0] * 8}
+    for g in GOLD:
+        yql = f"select * from s1 where {_nn()} AND {g['yql']}"
+        assert GpuTensorIndex._split_where(yql) == (True, g["yql"])
+        assert ix._is_tensor_query(yql, "embedding_similarity", qf)
+    multi = f"select * from s1 where ({_nn('marqo__embeddings_a')} OR {_nn('marqo__embeddings_b')}) AND {GOLD[0]['yql']}"
+    assert ix._is_tensor_query(multi, "embedding_similarity", qf)
+    assert ix._is_tensor_query(f"select * from s1 where {_nn()}", "embedding_similarity", qf)
+    # a structured index's filter (another grammar), lexical terms, other rank profiles: not answered here
+    assert not ix._is_tensor_query(f"select * from s1 where {_nn()} AND (price >= 3)", "embedding_similarity", qf)
+    assert not ix._is_tensor_query(f'select * from s1 where {_nn()} AND default contains "x"', "embedding_similarity", qf)
+    assert not ix._is_tensor_query(f"select * from s1 where {_nn()} AND {GOLD[0]['yql']}", "bm25", qf)
+    assert not ix._is_tensor_query(f'select * from s1 where default contains "x" AND {GOLD[0]["yql"]}',
+                                   "embedding_similarity", qf)
+
+
+class _NumpyRowStore:
+    """CPU stand-in with RowStore's interface and arithmetic contract (fp16 rows, closeness = 1 / (2 - q.e) in fp64,
+    order (score desc, doc asc), best chunk per document) — lets the adapter's host logic run without a device."""
+
+    def __init__(self, dim, metric="prenormalized-angular", device=0, capacity=0):
+        self.dim, self.rows, self.docs, self.attrs = dim, [], [], {}
+
+    def __len__(self):
+        return len(self.rows)
+
+    def add(self, vecs, doc_ids=None):
+        import numpy as np
+        for i, v in enumerate(np.asarray(vecs, np.float32)):
+            self.rows.append(v.astype(np.float16).astype(np.float64))
+            self.docs.append(int(doc_ids[i]) if doc_ids is not None else len(self.docs))
+
+    def delete_doc(self, doc_id):
+        self.docs = [-1 if d == doc_id else d for d in self.docs]
+
+    def set_attributes(self, column, doc_ids, values):
+        for i, d in enumerate(doc_ids):
+            if column == -1:
+                for col in self.attrs.values():
+                    col.pop(int(d), None)
+            elif values is None:
+                self.attrs.setdefault(column, {}).pop(int(d), None)
+            else:
+                self.attrs.setdefault(column, {})[int(d)] = float(values[i])
+
+    def _rank(self, q, k, mult=(), add=()):
+        import numpy as np
+        qh = np.asarray(q, np.float32).reshape(-1).astype(np.float16).astype(np.float64)
+        best = {}
+        for r, (v, d) in enumerate(zip(self.rows, self.docs)):
+            if d < 0:
+                continue
+            c = 1.0 / (2.0 - float(v @ qh))
+            if d not in best or c > best[d][0]:
+                best[d] = (c, r)
+        out = []
+        for d, (c, r) in best.items():
+            cells = [w * self.attrs[col][d] for col, w in mult if d in self.attrs.get(col, {})]
+            m = float(np.prod(cells)) if cells else 1.0
+            a = sum(w * self.attrs[col][d] for col, w in add if d in self.attrs.get(col, {}))
+            out.append((m * c + a, d, r))
+        out.sort(key=lambda t: (-t[0], t[1]))
+        doc = np.full((1, k), -1, np.int32)
+        row = np.full((1, k), -1, np.int32)
+        score = np.full((1, k), -np.inf)
+        for i, (sc, d, r) in enumerate(out[:k]):
+            doc[0, i], row[0, i], score[0, i] = d, r, sc
+        return doc, row, score
+
+    def search(self, q, k):
+        return self._rank(q, k)
+
+    def search_modified(self, q, k, mult=(), add=()):
+        return self._rank(q, k, mult, add)
+
+    def get_row(self, r):
+        return self.rows[r].astype("float32")
+
+    def close(self):
+        pass
+
+
+def test_filtered_search_scenario_on_the_cpu_stand_in(monkeypatch):
+    import marqo_b200.gpu_tensor_index as gti
+    from _filter_scenario import run_filtered_search_scenario
+    monkeypatch.setattr(gti, "RowStore", _NumpyRowStore)
+    run_filtered_search_scenario()
