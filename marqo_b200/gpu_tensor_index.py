@@ -35,6 +35,9 @@ from .errors import VespaError, VespaStatusError
 RANK_PROFILE_EMBEDDING_SIMILARITY = "embedding_similarity"   # */common.py
 RANK_PROFILE_EMBEDDING_SIMILARITY_MODIFIERS_2_9 = "embedding_similarity_modifiers"   # */common.py (index version < 2.10)
 SCORE_MODIFIERS_FIELD = "marqo__score_modifiers"             # */common.py SCORE_MODIFIERS
+# structured indexes split the cells over two tensors whose products / sums are multiplied / added together
+# (structured_vespa_index/common.py:3-5, structured_vespa_schema.py:256-262): one sparse tensor over their union
+SCORE_MODIFIER_FIELDS = (SCORE_MODIFIERS_FIELD, "marqo__score_modifiers_float", "marqo__score_modifiers_double_long")
 MULT_WEIGHTS_INPUTS = ("marqo__mult_weights_tensor", "marqo__mult_weights")   # core/constants.py:22-27
 ADD_WEIGHTS_INPUTS = ("marqo__add_weights_tensor", "marqo__add_weights")
 MAX_ATTRIBUTE_COLUMNS = 64
@@ -181,12 +184,16 @@ class GpuTensorIndex:
                         if mat.size and mat.ndim != 2:
                             raise ValueError(f"field {f}: ragged embeddings")
                         staged[f] = (keys, mat)
-                    cells = fields.get(SCORE_MODIFIERS_FIELD) or {}
-                    if isinstance(cells, dict) and "cells" in cells and isinstance(cells["cells"], (dict, list)):
-                        cells = cells["cells"]          # Vespa's verbose tensor JSON form
-                    if isinstance(cells, list):
-                        cells = {c["address"]["p"]: c["value"] for c in cells}
-                    attrs = {str(name): float(v) for name, v in cells.items()}
+                    attrs: Dict[str, float] = {}
+                    for tensor_field in SCORE_MODIFIER_FIELDS:
+                        cells = fields.get(tensor_field) or {}
+                        if isinstance(cells, dict) and "cells" in cells and isinstance(cells["cells"], (dict, list)):
+                            cells = cells["cells"]          # Vespa's verbose tensor JSON form
+                        if isinstance(cells, list):
+                            cells = {c["address"]["p"]: c["value"] for c in cells}
+                        for name, v in cells.items():
+                            # structured indexes keep float-typed modifier fields in a tensor<float>: fp32 cells
+                            attrs[str(name)] = float(np.float32(v)) if tensor_field.endswith("_float") else float(v)
                     for name, v in attrs.items():
                         if not math.isfinite(v):
                             raise ValueError(f"score modifier field {name}: value {v} is not finite")

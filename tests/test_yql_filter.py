@@ -179,3 +179,32 @@ def test_filtered_search_scenario_on_the_cpu_stand_in(monkeypatch):
     from _filter_scenario import run_filtered_search_scenario
     monkeypatch.setattr(gti, "RowStore", _NumpyRowStore)
     run_filtered_search_scenario()
+
+
+def test_structured_index_modifier_tensors_on_the_cpu_stand_in(monkeypatch):
+    """Structured indexes feed two modifier tensors (float / double_long, structured_vespa_index.py:217-230) and rank
+    with the product / sum over both (structured_vespa_schema.py:256-262): one sparse tensor over their union here."""
+    import numpy as np
+    import marqo_b200.gpu_tensor_index as gti
+    from _filter_scenario import _doc, _yql
+    monkeypatch.setattr(gti, "RowStore", _NumpyRowStore)
+    rng = np.random.default_rng(3)
+    vecs = rng.standard_normal((20, 64)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    ix = gti.GpuTensorIndex()
+    docs = [_doc(f"d{i}", {"marqo__id": f"d{i}", "marqo__score_modifiers_float": {"rating": 0.1 * (i % 5)},
+                           "marqo__score_modifiers_double_long": {"sold": i * 3}}, {"body": (["c"], vecs[i:i + 1])})
+            for i in range(20)]
+    assert not ix.feed_batch(docs, "s1").errors
+    q = vecs[7]
+    res = ix.query(_yql("s1", ["body"], 20), hits=20, ranking="embedding_similarity", model_restrict="s1",
+                   query_features={"marqo__query_embedding": q.tolist(), "marqo__mult_weights_tensor": {"rating": 2.0},
+                                   "marqo__add_weights_tensor": {"sold": 0.001}})
+    qh = q.astype(np.float16).astype(np.float64)
+    want = {}
+    for i in range(20):
+        c = 1.0 / (2.0 - float(vecs[i].astype(np.float16).astype(np.float64) @ qh))
+        want[f"d{i}"] = 2.0 * float(np.float32(0.1 * (i % 5))) * c + 0.001 * (i * 3)
+    order = sorted(want, key=lambda d: (-want[d], int(d[1:])))
+    assert [h.id.split("::")[-1] for h in res.hits] == order
+    assert all(abs(h.relevance - want[h.id.split("::")[-1]]) < 1e-12 for h in res.hits)
