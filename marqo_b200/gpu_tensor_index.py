@@ -4,9 +4,8 @@ Drop-in for `Config.vespa_client` (src/marqo/config.py:35) on the dense path: `f
 `delete_batch` keep the argument meaning and the response shapes of src/marqo/vespa/vespa_client.py:198-242,
 :267-296, :405-440, :468-500 and src/marqo/vespa/models/{query_result,feed_response,get_document_response,
 delete_document_response}.py.  Tensor queries (ranking == 'embedding_similarity', YQL made only of
-`nearestNeighbor(...)` terms, optionally followed by the ` AND <filter>` text of unstructured / semi-structured indexes) are
-answered from the GPU-resident fp16 matrix by the exact score + top-k kernels; everything else (bm25, hybrid, filters in
-another grammar) is handed to the optional `delegate` — a real VespaClient — or rejected with VespaError (SURVEY §8b:
+`nearestNeighbor(...)` terms, optionally followed by the ` AND <filter>` text either index type generates) are
+answered from the GPU-resident fp16 matrix by the exact score + top-k kernels; everything else (bm25, hybrid) is handed to the optional `delegate` — a real VespaClient — or rejected with VespaError (SURVEY §8b:
 "delegate ... rather than answer").
 
 Semantics implemented (from the schema generators the reference ships, executed inside Vespa today):
@@ -265,7 +264,7 @@ class GpuTensorIndex:
         if filter_text is not None:
             try:
                 compile_filter(filter_text)
-            except FilterSyntaxError:     # e.g. a structured index's filter grammar: not ours to answer
+            except FilterSyntaxError:     # text neither of the reference's filter generators emits: not ours to answer
                 return False
         qf = query_features or {}
         if not any(k in qf for k in QUERY_INPUT_EMBEDDINGS):

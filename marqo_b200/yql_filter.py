@@ -2,17 +2,21 @@
 src/marqo/core/unstructured_vespa_index/unstructured_vespa_index.py:62-66), for unstructured and semi-structured indexes
 (the latter reuses the same generator: semi_structured_vespa_index.py:67-69).
 
-Grammar — exactly what `UnstructuredVespaIndex._get_filter_term` emits (:135-226):
+Grammar — exactly what `UnstructuredVespaIndex._get_filter_term` (:135-226) and, for structured indexes,
+`StructuredVespaIndex._get_filter_term` (src/marqo/core/structured_vespa_index/structured_vespa_index.py:690-793) emit:
 
-    expr  := '(' expr ('AND' | 'OR') expr ... ')'  |  '!(' expr ')'  |  atom
-    atom  := '(' FIELD 'contains' STRING ')'                                             marqo__id, marqo__string_array
-           | '(' FIELD 'contains' 'sameElement(' 'key' 'contains' STRING ',' cond {',' cond} ')' ')'
+    expr  := '(' expr {('AND' | 'OR') expr} ')'  |  '!(' expr ')'  |  atom
+    atom  := FIELD 'contains' STRING                                       marqo__id, marqo__string_array, marqo__filter_<f>
+           | FIELD 'contains' 'sameElement(' 'key' 'contains' STRING ',' cond {',' cond} ')'       unstructured map fields
+           | FIELD ('>=' | '<=') NUMBER                                                              structured ranges
+           | FIELD 'in' '(' (STRING | NUMBER) {',' (STRING | NUMBER)} ')'                            structured IN
     cond  := 'value' 'contains' STRING  |  'value' ('=' | '>=' | '<=') NUMBER
 
-Semantics are Vespa's for the schema the reference generates (unstructured_vespa_schema.py:86-140): every filtered
-field is an attribute without `match: cased`, so string matching is whole-value and case-insensitive; `sameElement`
-requires key and value conditions to hold for the SAME map entry.  Anything outside this grammar (structured indexes use
-another one) raises FilterSyntaxError and the adapter delegates the query instead of answering it.
+Semantics are Vespa's for the schemas the reference generates (unstructured_vespa_schema.py:86-140,
+structured_vespa_schema.py:93-100): every filtered field is an attribute without `match: cased`, so string matching is
+whole-value and case-insensitive; `contains` on a numeric attribute is equality; a multi-value field matches when any
+element does; `sameElement` requires key and value conditions to hold for the SAME map entry.  Anything outside this
+grammar raises FilterSyntaxError and the adapter delegates the query instead of answering it.
 """
 from __future__ import annotations
 
@@ -25,6 +29,11 @@ class FilterSyntaxError(ValueError):
 
 
 _TOKEN = re.compile(r'\s*(?:("(?:[^"\\]|\\.)*")|(!\(|\(|\)|,|>=|<=|=)|([A-Za-z_][A-Za-z0-9_.]*)|(-?\d+(?:\.\d+)?(?:[eE][-+]?\d+)?))')
+
+# unstructured / semi-structured filter attributes (unstructured_vespa_index/common.py:3-13); structured ones are
+# `marqo__filter_<field>` (structured_vespa_schema.py:93-100)
+_FILTER_FIELDS = {"marqo__id", "marqo__short_string_fields", "marqo__string_array", "marqo__int_fields",
+                  "marqo__float_fields", "marqo__bool_fields"}
 
 Doc = Dict[str, Any]
 Pred = Callable[[Doc], bool]
@@ -67,24 +76,21 @@ class _Parser:
         self.i += 1
         return tok[1]
 
-    # expr := '!(' expr ')' | '(' ... ')'
     def expr(self) -> Pred:
         if self.peek() == ("sym", "!("):
             self.take()
             inner = self.expr()
             self.take("sym", ")")
             return lambda d: not inner(d)
+        if self.peek() != ("sym", "("):
+            return self.atom()
         self.take("sym", "(")
-        if self.peek()[0] == "word" and self.peek(1) == ("word", "contains"):
-            pred = self.atom()
-            self.take("sym", ")")
-            return pred
         terms, ops = [self.expr()], []
         while self.peek()[0] == "word" and self.peek()[1] in ("AND", "OR"):
             ops.append(self.take())
             terms.append(self.expr())
         self.take("sym", ")")
-        if len(set(ops)) > 1:   # the generator never mixes operators inside one pair of parentheses
+        if len(set(ops)) > 1:   # the generators never mix operators inside one pair of parentheses
             raise FilterSyntaxError("mixed AND / OR without parentheses")
         if not ops:
             return terms[0]
@@ -94,18 +100,25 @@ class _Parser:
 
     def atom(self) -> Pred:
         field = self.take("word")
+        if field not in _FILTER_FIELDS and not field.startswith("marqo__filter_"):
+            # e.g. `default contains "x"` is a LEXICAL term on the bm25 fieldset, not a filter
+            raise FilterSyntaxError(f"{field!r} is not a filter attribute")
+        if self.peek()[0] == "sym" and self.peek()[1] in (">=", "<="):
+            op, num = self.take(), float(self.take("num"))
+            return lambda d: any((_num(v) >= num) if op == ">=" else (_num(v) <= num) for v in _values(d.get(field)))
+        if self.peek() == ("word", "in"):
+            self.take()
+            self.take("sym", "(")
+            wanted = [self._literal()]
+            while self.peek() == ("sym", ","):
+                self.take()
+                wanted.append(self._literal())
+            self.take("sym", ")")
+            return lambda d: any(_equal(v, w) for v in _values(d.get(field)) for w in wanted)
         self.take("word", "contains")
         if self.peek()[0] == "str":
-            want = _fold(self.take("str"))
-
-            def whole(d: Doc) -> bool:
-                v = d.get(field)
-                if v is None:
-                    return False
-                if isinstance(v, (list, tuple)):
-                    return any(_fold(x) == want for x in v)
-                return _fold(v) == want
-            return whole
+            want = self.take("str")
+            return lambda d: any(_equal(v, want) for v in _values(d.get(field)))
         self.take("word", "sameElement")
         self.take("sym", "(")
         self.take("word", "key")
@@ -140,6 +153,29 @@ class _Parser:
                 return False
             return any(_fold(k) == key and all(c(v) for c in conds) for k, v in m.items())
         return same_element
+
+    def _literal(self):
+        kind, val = self.peek()
+        if kind == "str":
+            return self.take()
+        if kind == "num":
+            return float(self.take())
+        raise FilterSyntaxError(f"expected a string or a number, found {val!r}")
+
+
+def _values(v: Any) -> List[Any]:
+    if v is None:
+        return []
+    return list(v) if isinstance(v, (list, tuple)) else [v]
+
+
+def _equal(stored: Any, wanted: Any) -> bool:
+    """`contains` / `in` on an attribute: numeric fields compare as numbers, strings whole-value and uncased."""
+    if isinstance(stored, bool):
+        stored = int(stored)
+    if isinstance(stored, (int, float)):
+        return _num(wanted) == float(stored)
+    return not isinstance(wanted, float) and _fold(stored) == _fold(wanted)
 
 
 def _num(v: Any) -> float:

@@ -84,7 +84,7 @@ def run_filtered_search_scenario():
     assert [h.id.split("::")[-1] for h in resm.hits] == wantm[3:8]
     # another grammar: not answered
     with pytest.raises(VespaError):
-        ix.query(_yql("s1", ["body"], 5) + " AND (price >= 3)", hits=5, ranking="embedding_similarity",
+        ix.query(_yql("s1", ["body"], 5) + ' AND (title matches "x")', hits=5, ranking="embedding_similarity",
                  model_restrict="s1", query_features={"marqo__query_embedding": q.tolist()})
     ix.close()
 

@@ -70,11 +70,13 @@ def test_every_reference_filter_is_accepted_and_selects_the_right_documents():
 
 
 @pytest.mark.parametrize("bad", [
-    "price > 3",                                             # a structured-index filter: other grammar -> delegate
-    '(title contains "x") AND',
-    '((a contains "x") AND (b contains "y") OR (c contains "z"))',
+    "price > 3",                                             # not an operator either generator emits
+    '(marqo__id contains "x") AND',
+    '((marqo__id contains "x") AND (marqo__id contains "y") OR (marqo__id contains "z"))',
     '(marqo__int_fields contains sameElement(key contains "p"))',
-    '(x contains "unterminated)',
+    '(marqo__id contains "unterminated)',
+    'default contains "x"',                                  # a lexical term, not a filter attribute
+    '(title contains "x")',
 ])
 def test_other_grammars_are_rejected(bad):
     from marqo_b200.yql_filter import FilterSyntaxError, compile_filter
@@ -100,8 +102,8 @@ def test_adapter_recognises_filtered_tensor_queries():
     multi = f"select * from s1 where ({_nn('marqo__embeddings_a')} OR {_nn('marqo__embeddings_b')}) AND {GOLD[0]['yql']}"
     assert ix._is_tensor_query(multi, "embedding_similarity", qf)
     assert ix._is_tensor_query(f"select * from s1 where {_nn()}", "embedding_similarity", qf)
-    # a structured index's filter (another grammar), lexical terms, other rank profiles: not answered here
-    assert not ix._is_tensor_query(f"select * from s1 where {_nn()} AND (price >= 3)", "embedding_similarity", qf)
+    # text outside both generators' grammars, lexical terms, other rank profiles: not answered here
+    assert not ix._is_tensor_query(f'select * from s1 where {_nn()} AND (title matches "x")', "embedding_similarity", qf)
     assert not ix._is_tensor_query(f'select * from s1 where {_nn()} AND default contains "x"', "embedding_similarity", qf)
     assert not ix._is_tensor_query(f"select * from s1 where {_nn()} AND {GOLD[0]['yql']}", "bm25", qf)
     assert not ix._is_tensor_query(f'select * from s1 where default contains "x" AND {GOLD[0]["yql"]}',
@@ -208,3 +210,55 @@ def test_structured_index_modifier_tensors_on_the_cpu_stand_in(monkeypatch):
     order = sorted(want, key=lambda d: (-want[d], int(d[1:])))
     assert [h.id.split("::")[-1] for h in res.hits] == order
     assert all(abs(h.relevance - want[h.id.split("::")[-1]]) < 1e-12 for h in res.hits)
+
+
+STRUCTURED_GOLD = json.loads((Path(__file__).resolve().parent / "golden" / "filter_golden_structured.json").read_text())
+
+
+def _structured_fields(doc_id, logical):
+    """Logical document -> stored fields of a structured index whose fields all carry the Filter feature
+    (structured_vespa_index.py:183-215: the value goes under the field's filter_field_name; booleans as bytes)."""
+    f = {"marqo__id": doc_id}
+    for k, v in logical.items():
+        f[f"marqo__filter_{k}"] = int(v) if isinstance(v, bool) else v
+    return f
+
+
+STRUCTURED_DOCS = {
+    "d0": dict(color="red", price=15.0, in_stock=True, tags=["sale", "new"], year=2024, rating=4.5, title='say "hi"'),
+    "d1": dict(color="blue", price=25.0, in_stock=False, tags=["new"], year=2023, rating=3.0),
+    "d2": dict(color="dark red", price=10.5, in_stock=True, year=2024, rating=4.5),
+    "d3": dict(color="Red", price=3.0, in_stock=True, tags=["sale"]),
+    "doc7": dict(),
+}
+STRUCTURED_EXPECTED = {
+    "color:red": {"d0", "d3"},
+    "price:[10 TO 20]": {"d0", "d2"},
+    "price:[10.5 TO *]": {"d0", "d1", "d2"},
+    "price:[* TO 3]": {"d3"},
+    "in_stock:true": {"d0", "d2", "d3"},
+    "in_stock:false AND color:red": set(),
+    "color:red OR color:blue": {"d0", "d1", "d3"},
+    "NOT color:red": {"d1", "d2", "doc7"},
+    "(color:red OR color:blue) AND price:[0 TO 100]": {"d0", "d1", "d3"},
+    "NOT (color:red AND in_stock:true)": {"d1", "d2", "doc7"},
+    "tags:sale": {"d0", "d3"},
+    "year:2024": {"d0", "d2"},
+    "rating:4.5": {"d0", "d2"},
+    "_id:doc7": {"doc7"},
+    'title:(say \\"hi\\")': {"d0"},
+    "color in (red, blue)": {"d0", "d1", "d3"},
+    "year in (2023, 2024)": {"d0", "d1", "d2"},
+    "color:RED": {"d0", "d3"},
+    "NOT _id in (d0, d1)": {"d2", "d3", "doc7"},
+}
+
+
+def test_structured_index_filters_from_the_reference_generator():
+    from marqo_b200.yql_filter import compile_filter
+    assert {g["filter"] for g in STRUCTURED_GOLD} == set(STRUCTURED_EXPECTED)
+    stored = {doc_id: _structured_fields(doc_id, logical) for doc_id, logical in STRUCTURED_DOCS.items()}
+    for g in STRUCTURED_GOLD:
+        pred = compile_filter(g["yql"])
+        got = {doc_id for doc_id, fields in stored.items() if pred(fields)}
+        assert got == STRUCTURED_EXPECTED[g["filter"]], (g["filter"], g["yql"], got)
