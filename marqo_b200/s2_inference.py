@@ -19,6 +19,7 @@ from typing import Any, Dict, List, Optional, Sequence, Union
 import numpy as np
 
 from . import model_registry
+from .inference_cache import MarqoInferenceCache
 from .errors import (ConfigurationError, InternalError, InvalidModelPropertiesError, ModelCacheManagementError,
                      ModelLoadError, ModelNotInCacheError, UnknownModelError, VectoriseError)
 
@@ -187,18 +188,72 @@ def clear_loaded_models() -> None:
     _available_models.clear()
 
 
+def _inference_cache_from_env() -> MarqoInferenceCache:
+    """s2_inference.py:43-45; defaults: size 0 (disabled), LRU (tensor_search/configs.py)."""
+    raw = os.environ.get("MARQO_INFERENCE_CACHE_SIZE", "0")
+    try:
+        size = int(raw)
+    except ValueError:
+        raise ConfigurationError(f"MARQO_INFERENCE_CACHE_SIZE must be an integer, got {raw!r}")
+    return MarqoInferenceCache(cache_size=size, cache_type=os.environ.get("MARQO_INFERENCE_CACHE_TYPE", "LRU"))
+
+
+_marqo_inference_cache = _inference_cache_from_env()
+
+
 def vectorise(model_name: str, content, model_properties: dict = None, device: str = None,
               normalize_embeddings: bool = get_default_normalization(), model_auth=None, enable_cache: bool = False,
               modality: Modality = Modality.TEXT, **kwargs) -> List[List[float]]:
-    """s2_inference.py:48-69.  `enable_cache` is accepted for signature compatibility; the inference cache
-    (src/marqo/inference/inference_cache/) is a host dict owned by Marqo and is out of this engine's scope."""
+    """s2_inference.py:48-69"""
     if not device:
         raise InternalError(message="vectorise (internal function) cannot be called without setting device!")
     validated_model_properties = validate_model_properties(model_name, model_properties)
     model_cache_key = _create_model_cache_key(model_name, device, validated_model_properties)
     _update_available_models(model_cache_key, model_name, validated_model_properties, device, normalize_embeddings,
                              model_auth=model_auth)
+    if _marqo_inference_cache.is_enabled() and enable_cache:
+        return _vectorise_with_cache(model_cache_key, content, normalize_embeddings, modality, **kwargs)
     return _encode_without_cache(model_cache_key, content, normalize_embeddings, modality, **kwargs)
+
+
+def _vectorise_with_cache(model_cache_key: str, content, normalize_embeddings: bool, modality: Modality, **kwargs):
+    """s2_inference.py:72-119: only STRINGS are cached; a list call encodes its misses (and every non-string element)
+    in one batch, stores the string results, and puts the hits back at their positions."""
+    cache = _marqo_inference_cache
+    if isinstance(content, str):
+        hit = cache.get(model_cache_key, content)
+        if hit is not None:
+            return _convert_cached_embeddings_to_output(hit)
+        vectorised = _encode_without_cache(model_cache_key, content, normalize_embeddings, modality, **kwargs)
+        cache.set(model_cache_key, content, vectorised[0])
+        return vectorised
+    if not isinstance(content, list):
+        raise TypeError(f"Unsupported content type: {type(content).__name__}")
+    misses, hits = [], []
+    for loc, item in enumerate(content):
+        hit = cache.get(model_cache_key, item) if isinstance(item, str) else None
+        if hit is None:
+            misses.append(item)
+        else:
+            hits.append((loc, hit))
+    if not misses:
+        return [vector for _, vector in hits]
+    outputs = _encode_without_cache(model_cache_key, misses, normalize_embeddings, modality, **kwargs)
+    for item, vector in zip(misses, outputs):
+        if isinstance(item, str):
+            cache.set(model_cache_key, item, vector)
+    for loc, vector in hits:          # ascending positions: each insert lands where the hit was in `content`
+        outputs.insert(loc, vector)
+    return outputs
+
+
+def _convert_cached_embeddings_to_output(cached_embeddings: List[float]) -> List[List[float]]:
+    """s2_inference.py:689-705"""
+    if not isinstance(cached_embeddings, list):
+        raise TypeError(f"expected a list of floats but received {type(cached_embeddings)}")
+    if not isinstance(cached_embeddings[0], float):
+        raise TypeError(f"expected a list of floats but received {type(cached_embeddings[0])}")
+    return [cached_embeddings]
 
 
 def _is_tensor(x) -> bool:
