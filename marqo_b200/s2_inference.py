@@ -136,23 +136,91 @@ def _load_model(model_name: str, model_properties: dict, device: str, model_auth
     return model
 
 
+# Declared (not measured) model sizes in GB: src/marqo/s2_inference/constants.py:4-26; priorities
+# model_properties["model_size"] > model name > model type > default (get_model_size, s2_inference.py:504-517)
+MODEL_TYPE_SIZE_MAPPING = {"open_clip": 1, "clip": 1, "sbert": 0.7, "random": 0.1, "multilingual_clip": 5, "clip_onnx": 1,
+                           "sbert_onnx": 0.7, "hf": 1}
+MODEL_NAME_SIZE_MAPPING = {"vit-l-14": 1.5, "vit-g": 5, "vit-h": 5, "vit-bigg-14": 6}
+DEFAULT_MODEL_SIZE = 0.66
+DEFAULT_MAX_MODEL_MEMORY = 4   # GB per device, src/marqo/api/configs.py:35-36
+
+
+def get_model_size(model_name: str, model_properties: dict):
+    if "model_size" in model_properties:
+        return model_properties["model_size"]
+    name_info = (model_name + model_properties.get("name", "")).lower().replace("/", "-")
+    for name, size in MODEL_NAME_SIZE_MAPPING.items():
+        if name in name_info:
+            return size
+    return MODEL_TYPE_SIZE_MAPPING.get(_reference_type_name(model_properties.get("type", None)), DEFAULT_MODEL_SIZE)
+
+
+def _reference_type_name(t):
+    """this engine's loader types carry a b200_ prefix in the registry; sizes are declared per reference type"""
+    return {model_registry.TYPE_OPEN_CLIP: "open_clip", model_registry.TYPE_HF: "hf"}.get(t, t)
+
+
+def _check_memory_threshold_for_model(device: str, model_size) -> bool:
+    """s2_inference.py:460-501: sum of the DECLARED sizes of the models cached for this device + the new one must stay
+    below MARQO_MAX_CUDA_MODEL_MEMORY / MARQO_MAX_CPU_MODEL_MEMORY; a model larger than the threshold is refused."""
+    if device.startswith("cuda"):
+        keys = [k for k in _available_models if k.endswith(device)]
+        threshold = float(os.environ.get("MARQO_MAX_CUDA_MODEL_MEMORY", DEFAULT_MAX_MODEL_MEMORY))
+    elif device.startswith("cpu"):
+        keys = [k for k in _available_models if k.endswith("cpu")]
+        threshold = float(os.environ.get("MARQO_MAX_CPU_MODEL_MEMORY", DEFAULT_MAX_MODEL_MEMORY))
+    else:
+        raise ModelCacheManagementError(f"Unable to check the device cache for device=`{device}`.")
+    used_memory = sum(_available_models[k].get(AvailableModelsKey.model_size, DEFAULT_MODEL_SIZE) for k in keys)
+    if model_size > threshold:
+        raise ModelCacheManagementError(
+            f"You are trying to load a model with size = `{model_size}` into device = `{device}`, which is larger than "
+            f"the device threshold = `{threshold}`. Marqo CANNOT find enough space for the model. Please modify the "
+            f"threshold by setting the environment variable `MARQO_MAX_CUDA_MODEL_MEMORY` or `MARQO_MAX_CPU_MODEL_MEMORY`.")
+    return (used_memory + model_size) < threshold
+
+
+def _validate_model_into_device(model_name: str, model_properties: dict, device: str) -> bool:
+    """s2_inference.py:419-457: if the device's declared budget is exhausted, eject its models least-recently-used first
+    until the new one fits (here `close()` frees the engine handle's memory; the reference relies on del + gc)."""
+    model_size = get_model_size(model_name, model_properties)
+    if _check_memory_threshold_for_model(device, model_size):
+        return True
+    on_device = sorted((k for k in list(_available_models) if k.endswith(device)),
+                       key=lambda k: _available_models[k][AvailableModelsKey.most_recently_used_time])
+    for key in on_device:
+        entry = _available_models.pop(key)
+        model = entry.get(AvailableModelsKey.model)
+        if hasattr(model, "close"):
+            model.close()
+        if _check_memory_threshold_for_model(device, model_size):
+            return True
+    raise ModelCacheManagementError(
+        f"Marqo CANNOT find enough space to load model = `{model_name}` in device = `{device}`.\n"
+        f"Marqo tried to eject all the models on this device = `{device}` but still can't find enough space. \n"
+        f"Please use a smaller model or increase the memory threshold.")
+
+
 def _update_available_models(model_cache_key: str, model_name: str, validated_model_properties: dict, device: str,
                              normalize_embeddings: bool, model_auth=None) -> None:
-    """s2_inference.py:286-337: load on first use under the module lock, fail fast if another thread is loading."""
+    """s2_inference.py:286-337: load on first use under the module lock (after making room on the device), fail fast if
+    another thread is loading."""
     if model_cache_key not in _available_models:
+        model_size = get_model_size(model_name, validated_model_properties)
         if lock.locked():
             raise ModelCacheManagementError(
                 "Request rejected, as this request attempted to update the model cache, while "
                 "another request was updating the model cache at the same time. "
                 "Please wait for 10 seconds and send the request again ")
         with lock:
+            _validate_model_into_device(model_name, validated_model_properties, device)
             try:
                 now = datetime.datetime.now()
                 _available_models[model_cache_key] = {
                     AvailableModelsKey.model: _load_model(model_name, validated_model_properties, device=device,
                                                           model_auth=model_auth),
                     AvailableModelsKey.most_recently_used_time: now,
-                    AvailableModelsKey.model_size: validated_model_properties.get("model_size", 1),
+                    AvailableModelsKey.model_size: model_size,
                 }
             except Exception as e:
                 raise ModelLoadError(
