@@ -256,6 +256,33 @@ def clear_loaded_models() -> None:
     _available_models.clear()
 
 
+def is_preprocess_image_model(model_properties: dict = None) -> bool:
+    """s2_inference.py:180-185 (constants.PREPROCESS_IMAGE_MODEL_LIST = CLIP-type models; here: the open_clip loader)."""
+    return _reference_type_name((model_properties or {}).get("type")) in ("open_clip", "clip")
+
+
+def load_multimodal_model_and_get_preprocessors(model_name: str, model_properties: Optional[dict] = None,
+                                                device: Optional[str] = None, model_auth=None,
+                                                normalize_embeddings: bool = get_default_normalization()):
+    """s2_inference.py:193-235: what add_documents calls before downloading images — the loaded model plus the per-
+    modality preprocessors its download threads apply (add_docs.py:129-134).  For this engine `model.preprocess` only
+    decodes to uint8 HWC; resize / crop / normalise run on the GPU."""
+    if not device:
+        raise InternalError(message="vectorise (internal function) cannot be called without setting device!")
+    model_properties = validate_model_properties(model_name, model_properties)
+    model_cache_key = _create_model_cache_key(model_name, device, model_properties)
+    _update_available_models(model_cache_key, model_name, model_properties, device, normalize_embeddings,
+                             model_auth=model_auth)
+    model = _available_models[model_cache_key][AvailableModelsKey.model]
+    preprocessors = {
+        "image": getattr(model, "preprocess", None) if is_preprocess_image_model(model_properties) else None,
+        "video": None,
+        "audio": None,
+        "text": None,
+    }
+    return model, preprocessors
+
+
 def _inference_cache_from_env() -> MarqoInferenceCache:
     """s2_inference.py:43-45; defaults: size 0 (disabled), LRU (tensor_search/configs.py)."""
     raw = os.environ.get("MARQO_INFERENCE_CACHE_SIZE", "0")

@@ -42,3 +42,30 @@ def test_model_cache_management_matches_reference(case, monkeypatch):
         assert evicted and all(m.closed for m in evicted)      # ejected handles give their device memory back
     finally:
         s2._available_models.clear()
+
+
+def test_preprocessors_seam(monkeypatch):
+    """s2_inference.py:193-235: add_documents asks for (model, preprocessors) once per batch."""
+    from marqo_b200 import s2_inference as s2
+    from marqo_b200.errors import InternalError
+
+    class _Clip(_Dummy):
+        def preprocess(self, image):
+            return image
+
+    monkeypatch.setattr(s2, "_load_model", lambda name, props, device, model_auth=None: _Clip())
+    s2._available_models.clear()
+    try:
+        arch = {"any": 1}
+        model, pre = s2.load_multimodal_model_and_get_preprocessors(
+            "tiny-clip", {"name": "tiny-clip", "dimensions": 8, "type": "open_clip", "arch": arch}, device="cuda:0")
+        assert set(pre) == {"image", "video", "audio", "text"} and pre["image"] == model.preprocess
+        assert pre["video"] is None and pre["audio"] is None and pre["text"] is None
+        model2, pre2 = s2.load_multimodal_model_and_get_preprocessors(
+            "tiny-bert", {"name": "tiny-bert", "dimensions": 8, "type": "hf", "arch": arch}, device="cuda:0")
+        assert pre2["image"] is None                       # text models have no image preprocessor
+        assert len(s2._available_models) == 2
+        with pytest.raises(InternalError):
+            s2.load_multimodal_model_and_get_preprocessors("tiny-clip", {"dimensions": 8, "type": "open_clip"}, device=None)
+    finally:
+        s2._available_models.clear()
