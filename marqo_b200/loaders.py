@@ -124,6 +124,8 @@ class B200OpenCLIP:
         if len(items) == 0:
             raise UnidentifiedImageError("received empty list, expected at least one element.")
         S = self.model.image_size
+        if all(self._on_model_device(it) for it in items):
+            return self._encode_device_images(items, bool(normalize))
         u8, f32 = [], []
         for it in items:
             if isinstance(it, str):
@@ -151,6 +153,36 @@ class B200OpenCLIP:
         for (h, w), idx in groups.items():
             out[idx] = self.model.encode_images_u8_list([u8[i] for i in idx], normalize=bool(normalize))
         return out
+
+    def _on_model_device(self, it) -> bool:
+        """A uint8 HWC torch tensor already resident on this model's GPU — what Marqo's download threads produce:
+        `preprocessors['image'](image).to(device)` (add_docs.py:129-134)."""
+        return (_is_tensor(it) and getattr(it, "is_cuda", False) and it.device.index == self.model.device
+                and str(it.dtype) == "torch.uint8" and it.ndim == 3 and it.shape[2] == 3)
+
+    def _encode_device_images(self, items, normalize: bool) -> np.ndarray:
+        """Images that are already in HBM stay there: one device-side stack per image size, the device entry point,
+        one D2H copy of the [n, dim] result — no per-image round trip through the host."""
+        import torch
+        out = torch.empty((len(items), self.model.embed_dim), dtype=torch.float32, device=items[0].device)
+        groups: Dict[tuple, List[int]] = {}
+        for i, t in enumerate(items):
+            groups.setdefault((int(t.shape[0]), int(t.shape[1])), []).append(i)
+        for (h, w), idx in groups.items():
+            batch = torch.stack([items[i] for i in idx]).contiguous()
+            res = out if len(groups) == 1 else torch.empty((len(idx), self.model.embed_dim), dtype=torch.float32,
+                                                          device=batch.device)
+            self._sync_device(batch.device)      # the engine runs on its own stream: the stack must have landed
+            self.model.encode_images_u8_device(batch.data_ptr(), len(idx), h, w, res.data_ptr(), normalize=normalize,
+                                               sync=True)
+            if res is not out:
+                out[torch.as_tensor(idx, device=out.device)] = res
+        return out.cpu().numpy()
+
+    @staticmethod
+    def _sync_device(device) -> None:
+        import torch
+        torch.cuda.synchronize(device)
 
     def encode_text(self, sentence: Union[str, List[str]], normalize=True) -> np.ndarray:
         """open_clip_model.py:268-286"""

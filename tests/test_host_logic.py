@@ -304,3 +304,39 @@ def test_concurrent_model_load_is_rejected_like_the_reference(monkeypatch):
     # once loaded, concurrent encode() calls need no lock (the reference only locks loading, s2_inference.py:293-298)
     assert s2.vectorise("slow-a", ["x", "y"], model_properties=props_a, device="cuda:0") == [[1.0] * 4, [1.0] * 4]
     s2.clear_loaded_models()
+
+
+def test_clip_loader_keeps_device_images_on_the_device(monkeypatch):
+    """add_docs.py:129-134 hands encode() tensors that are already on the GPU; the loader must stack them there and call
+    the device entry point once per image size.  The plumbing is exercised here with host tensors standing in for device
+    ones (the 'device' pointers are then readable through ctypes)."""
+    import ctypes
+    import numpy as np
+    import torch
+    from marqo_b200.loaders import B200OpenCLIP
+
+    calls = []
+
+    class FakeEncoder:
+        device, embed_dim, image_size = 0, 4, 224
+
+        def encode_images_u8_device(self, d_ptr, n, h, w, d_out_ptr, normalize=True, sync=True):
+            img = np.ctypeslib.as_array((ctypes.c_uint8 * (n * h * w * 3)).from_address(d_ptr)).reshape(n, h, w, 3)
+            out = np.ctypeslib.as_array((ctypes.c_float * (n * 4)).from_address(d_out_ptr)).reshape(n, 4)
+            out[:] = np.stack([img.reshape(n, -1).sum(1), np.full(n, h), np.full(n, w), np.full(n, float(normalize))], 1)
+            calls.append((n, h, w, sync))
+
+    loader = B200OpenCLIP.__new__(B200OpenCLIP)
+    loader.model = FakeEncoder()
+    monkeypatch.setattr(B200OpenCLIP, "_on_model_device", lambda self, it: isinstance(it, torch.Tensor))
+    monkeypatch.setattr(B200OpenCLIP, "_sync_device", staticmethod(lambda device: None))
+    g = torch.Generator().manual_seed(0)
+    sizes = [(8, 8), (8, 8), (6, 10), (8, 8), (6, 10)]
+    imgs = [torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, generator=g) for h, w in sizes]
+    out = loader.encode_image(imgs, normalize=True)
+    assert out.shape == (5, 4) and sorted(calls) == [(2, 6, 10, True), (3, 8, 8, True)]
+    for i, (h, w) in enumerate(sizes):                      # every row landed at its own position
+        assert out[i].tolist() == [float(imgs[i].sum()), h, w, 1.0]
+    calls.clear()
+    out1 = loader.encode_image(imgs[:2], normalize=False)   # one size: written straight into the result block
+    assert calls == [(2, 8, 8, True)] and out1[:, 3].tolist() == [0.0, 0.0]
