@@ -43,6 +43,9 @@ FILTERS = [
     'title:(say \\"hi\\")',
     "a:1 AND (b:2 OR (c:3 AND NOT d:4))",
     "color:RED",
+    # Recommender._get_exclusion_filter (core/search/recommender.py:205-214), alone and on top of a user filter
+    "NOT (_id:(d0) OR _id:(d1) OR _id:(d2))",
+    "(color:red) AND NOT (_id:(d0) OR _id:(doc7))",
 ]
 out = []
 parser = MarqoFilterStringParser()

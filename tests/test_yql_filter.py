@@ -56,6 +56,8 @@ EXPECTED = {
     'title:(say \\"hi\\")': {"d0"},
     "a:1 AND (b:2 OR (c:3 AND NOT d:4))": {"d0", "d1"},
     "color:RED": {"d0", "d3"},
+    "NOT (_id:(d0) OR _id:(d1) OR _id:(d2))": {"d3", "doc7"},
+    "(color:red) AND NOT (_id:(d0) OR _id:(doc7))": {"d3"},
 }
 
 
