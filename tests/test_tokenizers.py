@@ -252,7 +252,7 @@ def test_property_random_unicode_text(wp, clip):
                       st.sampled_from(list(" \t\n.,!?'&#;[]<>_-") + ["[SEP]", "[MASK]", "&amp;", "&#x41;", "'s", "Σ"]))
     text = st.lists(piece, max_size=40).map("".join)
 
-    @settings(max_examples=300, deadline=None)
+    @settings(max_examples=int(__import__('os').environ.get('TOKENIZER_FUZZ_EXAMPLES', '300')), deadline=None, derandomize=True)
     @given(st.lists(text, min_size=1, max_size=6))
     def check(texts):
         got = mine_wp(texts, max_length=24)
