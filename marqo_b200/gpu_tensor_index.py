@@ -197,8 +197,8 @@ class GpuTensorIndex:
                         if not math.isfinite(v):
                             raise ValueError(f"score modifier field {name}: value {v} is not finite")
                         if name not in s.attr_col:
-                            if len(s.attr_col) >= MAX_ATTRIBUTE_COLUMNS:
-                                raise ValueError(f"more than {MAX_ATTRIBUTE_COLUMNS} distinct score-modifier fields")
+                            if len(s.attr_col) >= MAX_ATTRIBUTE_COLUMNS - 1:     # the last column is the filter mask
+                                raise ValueError(f"more than {MAX_ATTRIBUTE_COLUMNS - 1} distinct score-modifier fields")
                             s.attr_col[name] = len(s.attr_col)
                     num = s.doc_num.get(doc_id)
                     if num is None:
@@ -392,7 +392,10 @@ class GpuTensorIndex:
                     exhausted = len(found) < fetch
                     if len(kept) < k and not exhausted:
                         if fetch >= self.MAX_FETCH:
-                            raise NativeError(ERR_UNSUPPORTED, f"filter leaves fewer than {k} of the best {fetch} documents")
+                            # a very selective filter: evaluate it over the whole schema once and let the scan skip
+                            # the excluded documents (one pass instead of ever deeper fetches)
+                            found = self._masked_search(s, store, q, k, allowed, mult_cols, add_cols)
+                            break
                         fetch = min(self.MAX_FETCH, fetch * 4)
                         continue
                     found = kept[:k]
@@ -417,6 +420,27 @@ class GpuTensorIndex:
             children.append({"id": f"id:{schema}:{schema}::{s.doc_ids[num]}", "relevance": sc, "source": "content_default",
                              "fields": out_fields})
         return children
+
+    MASK_COLUMN = MAX_ATTRIBUTE_COLUMNS - 1     # reserved attribute column: the per-query exclusion mask
+    MASK_PENALTY = -1.0e30                      # addend of an excluded document: it can only rank after every kept one
+
+    def _masked_search(self, s: _Schema, store: RowStore, q: np.ndarray, k: int, allowed, mult_cols, add_cols):
+        """Exact top-k of the kept documents in one scan: excluded documents get an additive score modifier of -1e30
+        through the reserved attribute column (set for this query, removed afterwards), so they sort after every kept
+        document and are dropped from the result."""
+        if len(s.attr_col) >= MAX_ATTRIBUTE_COLUMNS or len(add_cols) >= MAX_MODIFIER_TERMS:
+            raise NativeError(ERR_UNSUPPORTED, "no free attribute column / modifier term for the filter mask")
+        excluded = [num for num, doc_id in enumerate(s.doc_ids) if doc_id is not None and not allowed(num)]
+        try:
+            if excluded:
+                store.set_attributes(self.MASK_COLUMN, excluded, [1.0] * len(excluded))
+            doc, row, score = store.search_modified(q[None, :], k, mult_cols,
+                                                    list(add_cols) + [(self.MASK_COLUMN, self.MASK_PENALTY)])
+        finally:
+            if excluded:
+                store.set_attributes(self.MASK_COLUMN, excluded, None)
+        return [(int(d), int(r), float(sc)) for d, r, sc in zip(doc[0], row[0], score[0])
+                if d >= 0 and sc > self.MASK_PENALTY / 2]
 
     def _distance_from_closeness(self, closeness: float) -> float:
         if self.metric == "dotproduct":

@@ -264,3 +264,42 @@ def test_structured_index_filters_from_the_reference_generator():
         pred = compile_filter(g["yql"])
         got = {doc_id for doc_id, fields in stored.items() if pred(fields)}
         assert got == STRUCTURED_EXPECTED[g["filter"]], (g["filter"], g["yql"], got)
+
+
+def test_very_selective_filters_switch_to_one_masked_scan(monkeypatch):
+    """When deeper fetches hit their cap the adapter evaluates the filter over the whole schema and excludes documents
+    through the reserved attribute column — same exact answer, one scan.  The cap is lowered to force that path."""
+    import numpy as np
+    import marqo_b200.gpu_tensor_index as gti
+    from _filter_scenario import _doc, _yql
+    monkeypatch.setattr(gti, "RowStore", _NumpyRowStore)
+    monkeypatch.setattr(gti.GpuTensorIndex, "MAX_FETCH", 16)
+    rng = np.random.default_rng(5)
+    n = 200
+    vecs = rng.standard_normal((n, 64)).astype(np.float32)
+    vecs /= np.linalg.norm(vecs, axis=1, keepdims=True)
+    ix = gti.GpuTensorIndex()
+    docs = [_doc(f"d{i}", {"marqo__id": f"d{i}", "marqo__int_fields": {"bucket": i % 50},
+                           "marqo__score_modifiers": {"pop": float(i % 3 + 1)}}, {"body": (["c"], vecs[i:i + 1])})
+            for i in range(n)]
+    assert not ix.feed_batch(docs, "s1").errors
+    q = vecs[3]
+    qh = q.astype(np.float16).astype(np.float64)
+    c = {f"d{i}": 1.0 / (2.0 - float(vecs[i].astype(np.float16).astype(np.float64) @ qh)) for i in range(n)}
+    flt = '((marqo__int_fields contains sameElement(key contains "bucket", value = 7)) OR ' \
+          '(marqo__float_fields contains sameElement(key contains "bucket", value = 7)))'        # 4 of 200 documents
+    res = ix.query(_yql("s1", ["body"], 10) + f" AND {flt}", hits=10, ranking="embedding_similarity", model_restrict="s1",
+                   query_features={"marqo__query_embedding": q.tolist()})
+    want = sorted((d for d in c if int(d[1:]) % 50 == 7), key=lambda d: (-c[d], int(d[1:])))
+    assert [h.id.split("::")[-1] for h in res.hits] == want and len(want) == 4
+    assert all(abs(h.relevance - c[h.id.split("::")[-1]]) < 1e-12 for h in res.hits)
+    # together with score modifiers; and the mask column is gone afterwards (an unfiltered query sees every document)
+    resm = ix.query(_yql("s1", ["body"], 3) + f" AND {flt}", hits=3, ranking="embedding_similarity", model_restrict="s1",
+                    query_features={"marqo__query_embedding": q.tolist(), "marqo__add_weights_tensor": {"pop": 0.5}})
+    wantm = sorted(want, key=lambda d: (-(c[d] + 0.5 * (int(d[1:]) % 3 + 1)), int(d[1:])))[:3]
+    assert [h.id.split("::")[-1] for h in resm.hits] == wantm
+    plain = ix.query(_yql("s1", ["body"], 5), hits=5, ranking="embedding_similarity", model_restrict="s1",
+                     query_features={"marqo__query_embedding": q.tolist()})
+    assert [h.id.split("::")[-1] for h in plain.hits] == sorted(c, key=lambda d: (-c[d], int(d[1:])))[:5]
+    store = next(iter(ix._schemas["s1"].stores.values()))
+    assert not store.attrs.get(gti.GpuTensorIndex.MASK_COLUMN)
