@@ -303,3 +303,22 @@ def test_very_selective_filters_switch_to_one_masked_scan(monkeypatch):
     assert [h.id.split("::")[-1] for h in plain.hits] == sorted(c, key=lambda d: (-c[d], int(d[1:])))[:5]
     store = next(iter(ix._schemas["s1"].stores.values()))
     assert not store.attrs.get(gti.GpuTensorIndex.MASK_COLUMN)
+
+
+def test_index_scenarios_on_the_cpu_stand_in(monkeypatch):
+    """The GPU adapter tests' scenarios (feed / query / highlights / offset / overwrite / get_batch / delete / bad documents;
+    score modifiers incl. the refused negative multiplier) against the numpy stand-in."""
+    import marqo_b200.gpu_tensor_index as gti
+    from marqo_b200 import _native as N
+    from _filter_scenario import run_feed_query_scenario, run_score_modifier_scenario
+
+    class _Store(_NumpyRowStore):
+        def search_modified(self, q, k, mult=(), add=()):
+            # the engine refuses negative multipliers on indexes with explicit document ids (b200_index_search_modified)
+            if any(w * v < 0 for col, w in mult for v in self.attrs.get(col, {}).values()):
+                raise N.NativeError(N.ERR_UNSUPPORTED, "negative multiplier")
+            return super().search_modified(q, k, mult, add)
+
+    monkeypatch.setattr(gti, "RowStore", _Store)
+    run_feed_query_scenario()
+    run_score_modifier_scenario()
