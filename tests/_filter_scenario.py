@@ -230,43 +230,3 @@ def run_score_modifier_scenario():
         ix.query(_yql("s1", ["body"], 10), hits=10, ranking="embedding_similarity", model_restrict="s1",
                  query_features={"marqo__query_embedding": q.tolist(), "marqo__mult_weights_lexical": {"popularity": 1.0}})
     ix.close()
-
-
-def test_gpu_tensor_index_snapshot_restart(gpu_required, tmp_path):
-    """f4 corpus persistence: save -> load on a fresh object gives the same hits, highlights, modifiers, get_batch."""
-    from marqo_b200.gpu_tensor_index import GpuTensorIndex, gather_documents_from_response
-    rng = np.random.default_rng(21)
-    D = 64
-
-    def unit(m):
-        x = rng.standard_normal((m, D)).astype(np.float32)
-        return x / np.linalg.norm(x, axis=1, keepdims=True)
-
-    ix = GpuTensorIndex()
-    docs = [_doc(f"d{i}", {"marqo__id": f"d{i}", "n": i, "marqo__score_modifiers": {"pop": float(i % 5 + 1)}},
-                 {"title": ([f"t{i}"], unit(1)), "body": ([f"b{i}.{j}" for j in range(2)], unit(2))}) for i in range(30)]
-    ix.feed_batch(docs, "s1")
-    ix.delete_batch(["d4"], "s1")
-    ix.feed_batch([_doc("d9", {"marqo__id": "d9", "n": 900}, {"title": (["new"], unit(1))})], "s1")   # overwrite
-    q = unit(1)[0]
-    plain = {"marqo__query_embedding": q.tolist()}
-    mod = dict(plain, marqo__mult_weights_tensor={"pop": 0.7}, marqo__add_weights_tensor={"pop": 0.01})
-    before = [ix.query(_yql("s1", ["title", "body"], 8), hits=8, ranking="embedding_similarity", model_restrict="s1",
-                       query_features=f) for f in (plain, mod)]
-    ix.save(str(tmp_path / "snap"))
-    ix.close()
-    again = GpuTensorIndex.load(str(tmp_path / "snap"))
-    after = [again.query(_yql("s1", ["title", "body"], 8), hits=8, ranking="embedding_similarity", model_restrict="s1",
-                         query_features=f) for f in (plain, mod)]
-    for b, a in zip(before, after):
-        assert [h.id for h in b.hits] == [h.id for h in a.hits]
-        assert [h.relevance for h in b.hits] == [h.relevance for h in a.hits]
-        assert gather_documents_from_response(b) == gather_documents_from_response(a)
-    assert again.get_document_count("s1") == 29
-    got = again.get_batch(["d9", "d4"], "s1")
-    assert got.responses[0].status == 200 and got.responses[0].document.fields["n"] == 900
-    assert got.responses[1].status == 404
-    # the restored index keeps accepting documents
-    assert not again.feed_batch([_doc("fresh", {"marqo__id": "fresh"}, {"title": (["x"], unit(1))})], "s1").errors
-    assert again.get_document_count("s1") == 30
-    again.close()
