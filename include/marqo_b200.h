@@ -88,14 +88,30 @@ int b200_index_add(b200_index* ix, const float* vecs, const int32_t* doc_ids, in
 /* Same, source already on the index's device (fp32 [m, dim]); used by the add_documents fast
  * path that never materialises List[List[float]] on the host. */
 int b200_index_add_device(b200_index* ix, const float* d_vecs, const int32_t* d_doc_ids, int64_t m);
+/* Same with the embeddings on the device (straight out of b200_model_encode_*_device) and the document numbers on the
+ * host: the add_documents fast path — vectors never visit the host, the small id list does not need a device buffer
+ * of the caller's (core/vespa_index/add_documents_handler.py:160-177 feeds what
+ * core/inference/tensor_fields_container.py:196-223 collected). */
+int b200_index_add_device_docs(b200_index* ix, const float* d_vecs, const int32_t* doc_ids, int64_t m);
+/* Rows whose values are not finite or do not fit the fp16 row store (|x| > 65504 after the angular metric's
+ * normalisation) are rejected by all three add calls with B200_ERR_INVALID_ARG; nothing of the batch is kept. */
 /* Tombstone every row of a document (add_documents replaces by _id:
- * src/marqo/core/vespa_index/add_documents_handler.py:140,258). */
+ * src/marqo/core/vespa_index/add_documents_handler.py:140,258).  O(rows): prefer b200_index_delete_rows when the
+ * caller knows the document's rows. */
 int b200_index_delete_doc(b200_index* ix, int32_t doc_id);
+/* Tombstone the listed rows (the adapter keeps document -> rows): one small scatter per batch of replaced / deleted
+ * documents instead of a corpus-wide pass per document. */
+int b200_index_delete_rows(b200_index* ix, const int32_t* rows, int64_t n);
+/* Squeeze tombstoned rows out of the matrix.  out_new_of_old: caller buffer of (current) num_rows int32 — the new row
+ * number of every old row, -1 for a dead one; *out_rows = rows left.  Row numbers returned by earlier searches are
+ * invalid afterwards. */
+int b200_index_compact(b200_index* ix, int32_t* out_new_of_old, int64_t* out_rows);
 int b200_index_num_rows(b200_index* ix, int64_t* out_rows);
 int b200_index_info(b200_index* ix, int* out_dim, int* out_metric, int* out_device);
 /* Copy row `row` back as fp32 (get_batch / use_existing_tensors:
  * add_documents_handler.py:160-165). */
 int b200_index_get_row(b200_index* ix, int64_t row, float* out_vec);
+int b200_index_get_rows(b200_index* ix, const int64_t* rows, int64_t n, float* out_vecs);
 
 /* Exact search.  q: fp32 host [nq, dim].  For every query returns the k best DOCUMENTS under
  *   score(doc) = max over the document's live rows of closeness(q, row)
@@ -106,10 +122,42 @@ int b200_index_get_row(b200_index* ix, int64_t row, float* out_vec);
  * rescored dot product. */
 int b200_index_search(b200_index* ix, const float* q, int nq, int k, int32_t* out_doc, int32_t* out_row,
                       double* out_score);
+/* How exactness is guaranteed (score.cu header): the tensor-core pass only SELECTS candidates, which are re-scored in
+ * fp64; a per-query guard proves that no row outside the candidate set can reach the k-th exact score, and queries
+ * that fail it (exact ties / near-ties across the candidate boundary, k beyond the per-SM lists) are answered by a
+ * second threshold-collect pass over the corpus.  k <= 160 is normally ONE pass; any k <= 11000 is supported
+ * (limit <= 1000 and offset <= 10000: src/marqo/api/configs.py:24-25). */
 /* Same with queries and outputs resident on the index's device; asynchronous on the handle's
- * stream unless sync != 0. */
+ * stream unless sync != 0.  With sync == 0 one fallback pass is enqueued unconditionally (it exits at once when no
+ * query needs it); a query that would need MORE than one fallback pass cannot be driven from the host then —
+ * b200_index_search_stats reports how often that happened (out_unresolved; 0 in every test and benchmark). */
 int b200_index_search_device(b200_index* ix, const float* d_q, int nq, int k, int32_t* d_out_doc,
                              int32_t* d_out_row, double* d_out_score, int sync);
+/* Counters since creation: groups of <= 64 queries searched, queries that failed the guard, fallback passes run by
+ * the synchronous entry points, groups the asynchronous entry point left unresolved.  Any pointer may be NULL. */
+int b200_index_search_stats(b200_index* ix, int64_t* out_groups, int64_t* out_flagged, int64_t* out_collect_passes,
+                            int64_t* out_unresolved);
+
+/* Search options: score modifiers (below) and a document FILTER.  filter_bits is a host bitset over LOCAL document
+ * numbers (bit d of word d/32 set = document d may match; documents >= filter_docs are excluded): the adapter compiles
+ * the ` AND <filter>` text Marqo appends to a tensor query (unstructured_vespa_index.py:59-66,135-226;
+ * structured_vespa_index.py:690-793) to this bitset once per distinct filter string and the scan applies it where it
+ * reads the row -> document map, next to the tombstone check — a filtered query costs one pass, whatever its
+ * selectivity.  filter_tag != 0 names the bitset: the device copy is reused while tag and filter_docs repeat. */
+typedef struct b200_search_opts {
+    const int32_t* mult_cols;
+    const double* mult_w;
+    int32_t n_mult;
+    const int32_t* add_cols;
+    const double* add_w;
+    int32_t n_add;
+    const uint32_t* filter_bits;
+    int64_t filter_docs;
+    uint64_t filter_tag;
+} b200_search_opts;
+/* b200_index_search with options (opts == NULL: plain search). */
+int b200_index_search_ex(b200_index* ix, const float* q, int nq, int k, const b200_search_opts* opts, int32_t* out_doc,
+                         int32_t* out_row, double* out_score);
 
 /* Score modifiers.  Per-document numeric attributes: the `marqo__score_modifiers`
  * tensor<double>(p{}) field every document is fed with
@@ -120,6 +168,9 @@ int b200_index_search_device(b200_index* ix, const float* d_q, int nq, int k, in
  * column (document overwritten or deleted).  Document numbers are LOCAL (before b200_index_set_doc_offset). */
 #define B200_MAX_ATTRIBUTE_COLUMNS 64
 int b200_index_set_attributes(b200_index* ix, int column, const int32_t* doc_ids, const double* values, int64_t n);
+/* Many (column, document, value) cells in one call — one feed_batch, one launch. */
+int b200_index_set_attributes_multi(b200_index* ix, const int32_t* columns, const int32_t* doc_ids, const double* values,
+                                    int64_t n);
 /* b200_index_search with the rank-profile function
  *   modify(score, mult_weights, add_weights) =
  *       if(count(mult_weights * attr) == 0, 1, reduce(mult_weights * attr, prod)) * score + reduce(add_weights * attr, sum)
@@ -148,6 +199,22 @@ int b200_index_set_doc_offset(b200_index* ix, int32_t offset);
  * outputs point into one 16*nq*k-byte buffer); blocks are nq*k*16 bytes apart.  nshards*k <= 256. */
 int b200_topk_merge_device(b200_index* ix, const void* d_gathered, int nshards, int nq, int k, int32_t* d_out_doc,
                            int32_t* d_out_row, double* d_out_score, int sync);
+/* Fused exchange + merge over NVLink peer memory (SURVEY §8e "peer-stores into a symmetric buffer in the top-k
+ * epilogue"): one process per GPU; every rank creates an exchange buffer, the ranks swap the 64-byte handles through
+ * whatever transport they have (torch.distributed all_gather of a byte tensor), open each other's buffers, and then
+ * b200_index_search_exchange = local search + ONE kernel that stores the packed [nq, k] block into every peer's
+ * buffer, publishes it with a release flag, waits for the peers' blocks and merges them — no NCCL call on the query
+ * path.  All ranks must call it the same number of times with the same nq and k (nq <= 64, world * k <= 256). */
+typedef struct b200_exchange b200_exchange;
+#define B200_EXCHANGE_HANDLE_BYTES 64
+int b200_exchange_create(int device, int rank, int world, int max_nq, int max_k, b200_exchange** out,
+                         void* out_handle /* B200_EXCHANGE_HANDLE_BYTES */);
+/* handles: world * B200_EXCHANGE_HANDLE_BYTES bytes, rank order (this rank's own entry is ignored). */
+int b200_exchange_open(b200_exchange* ex, const void* handles);
+int b200_exchange_destroy(b200_exchange* ex);
+/* d_local_block: device scratch of nq * k * 16 bytes (this rank's packed block); outputs [nq, k] on the device. */
+int b200_index_search_exchange(b200_index* ix, b200_exchange* ex, const float* d_q, int nq, int k, void* d_local_block,
+                               int32_t* d_out_doc, int32_t* d_out_row, double* d_out_score, int sync);
 /* Merge `nshards` per-shard result lists ([nshards, nq, k] each, host) into the global top-k
  * with the same total order; doc ids must already be global.  Used after the NCCL all-gather
  * of per-shard lists. */

@@ -45,6 +45,17 @@ class ModelDesc(C.Structure):
     ]
 
 
+class SearchOpts(C.Structure):
+    """b200_search_opts (include/marqo_b200.h)."""
+    _fields_ = [
+        ("mult_cols", C.c_void_p), ("mult_w", C.c_void_p), ("n_mult", C.c_int32),
+        ("add_cols", C.c_void_p), ("add_w", C.c_void_p), ("n_add", C.c_int32),
+        ("filter_bits", C.c_void_p), ("filter_docs", C.c_int64), ("filter_tag", C.c_uint64),
+    ]
+
+
+EXCHANGE_HANDLE_BYTES = 64
+
 _P = C.c_void_p
 _SIGNATURES = {
     "b200_abi_version": (C.c_int, []),
@@ -56,7 +67,19 @@ _SIGNATURES = {
     "b200_index_destroy": (C.c_int, [_P]),
     "b200_index_add": (C.c_int, [_P, _P, _P, C.c_int64]),
     "b200_index_add_device": (C.c_int, [_P, _P, _P, C.c_int64]),
+    "b200_index_add_device_docs": (C.c_int, [_P, _P, _P, C.c_int64]),
     "b200_index_delete_doc": (C.c_int, [_P, C.c_int32]),
+    "b200_index_delete_rows": (C.c_int, [_P, _P, C.c_int64]),
+    "b200_index_compact": (C.c_int, [_P, _P, C.POINTER(C.c_int64)]),
+    "b200_index_get_rows": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "b200_index_search_ex": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(SearchOpts), _P, _P, _P]),
+    "b200_index_search_stats": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                          C.POINTER(C.c_int64)]),
+    "b200_index_set_attributes_multi": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
+    "b200_exchange_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P), _P]),
+    "b200_exchange_open": (C.c_int, [_P, _P]),
+    "b200_exchange_destroy": (C.c_int, [_P]),
+    "b200_index_search_exchange": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int]),
     "b200_index_num_rows": (C.c_int, [_P, C.POINTER(C.c_int64)]),
     "b200_index_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b200_index_get_row": (C.c_int, [_P, C.c_int64, _P]),

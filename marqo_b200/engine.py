@@ -77,8 +77,25 @@ class RowStore:
         N.check(self._lib.b200_index_add_device(self._handle(), C.c_void_p(d_vecs_ptr),
                                                 C.c_void_p(d_doc_ids_ptr) if d_doc_ids_ptr else None, int(m)))
 
+    def add_device_docs(self, d_vecs_ptr: int, doc_ids: Sequence[int]) -> None:
+        """Embeddings already on the device (fp32 [m, dim]), document numbers on the host: the add_documents fast path."""
+        d = _as(doc_ids, np.int32)
+        N.check(self._lib.b200_index_add_device_docs(self._handle(), C.c_void_p(d_vecs_ptr), _ptr(d), d.shape[0]))
+
     def delete_doc(self, doc_id: int) -> None:
         N.check(self._lib.b200_index_delete_doc(self._handle(), int(doc_id)))
+
+    def delete_rows(self, rows: Sequence[int]) -> None:
+        r = _as(rows, np.int32)
+        N.check(self._lib.b200_index_delete_rows(self._handle(), _ptr(r), r.shape[0]))
+
+    def compact(self) -> np.ndarray:
+        """Squeeze tombstoned rows out; -> new_of_old int32 [old rows] (-1 = removed)."""
+        n = len(self)
+        m = np.empty(n, np.int32)
+        left = C.c_int64(0)
+        N.check(self._lib.b200_index_compact(self._handle(), _ptr(m), C.byref(left)))
+        return m
 
     # -- queries --------------------------------------------------------------------------------
     def __len__(self) -> int:
@@ -91,8 +108,19 @@ class RowStore:
         N.check(self._lib.b200_index_get_row(self._handle(), int(row), _ptr(out)))
         return out
 
-    def search(self, queries, k: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-        """-> (doc [nq,k] int32, row [nq,k] int32, closeness [nq,k] float64); unused slots are -1/-1/-inf."""
+    def get_rows(self, rows: Sequence[int]) -> np.ndarray:
+        r = _as(rows, np.int64)
+        out = np.empty((r.shape[0], self.dim), dtype=np.float32)
+        N.check(self._lib.b200_index_get_rows(self._handle(), _ptr(r), r.shape[0], _ptr(out)))
+        return out
+
+    def search(self, queries, k: int, mult: Sequence[Tuple[int, float]] = (), add: Sequence[Tuple[int, float]] = (),
+               filter_bits: Optional[np.ndarray] = None, filter_docs: int = 0,
+               filter_tag: int = 0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """-> (doc [nq,k] int32, row [nq,k] int32, score [nq,k] float64); unused slots are -1/-1/-inf.
+        mult / add: score modifiers [(attribute column, weight), ...] (score = modified score then);
+        filter_bits: uint32 bitset over document numbers (bit set = may match), covering filter_docs documents;
+        filter_tag != 0 lets the device keep the bitset between calls."""
         q = _as(queries, np.float32)
         if q.ndim == 1:
             q = q[None, :]
@@ -102,8 +130,33 @@ class RowStore:
         doc = np.empty((nq, k), dtype=np.int32)
         row = np.empty((nq, k), dtype=np.int32)
         score = np.empty((nq, k), dtype=np.float64)
-        N.check(self._lib.b200_index_search(self._handle(), _ptr(q), nq, int(k), _ptr(doc), _ptr(row), _ptr(score)))
+        opts = None
+        keep = []
+        if mult or add or filter_bits is not None:
+            o = N.SearchOpts()
+            mc = _as([c for c, _ in mult], np.int32)
+            mw = _as([w for _, w in mult], np.float64)
+            ac = _as([c for c, _ in add], np.int32)
+            aw = _as([w for _, w in add], np.float64)
+            keep = [mc, mw, ac, aw]
+            o.mult_cols, o.mult_w, o.n_mult = mc.ctypes.data, mw.ctypes.data, len(mc)
+            o.add_cols, o.add_w, o.n_add = ac.ctypes.data, aw.ctypes.data, len(ac)
+            if filter_bits is not None:
+                fb = _as(filter_bits, np.uint32)
+                if fb.shape[0] * 32 < filter_docs:
+                    raise ValueError("filter_bits does not cover filter_docs documents")
+                keep.append(fb)
+                o.filter_bits, o.filter_docs, o.filter_tag = fb.ctypes.data, int(filter_docs), int(filter_tag)
+            opts = C.byref(o)
+        N.check(self._lib.b200_index_search_ex(self._handle(), _ptr(q), nq, int(k), opts, _ptr(doc), _ptr(row),
+                                               _ptr(score)))
+        del keep
         return doc, row, score
+
+    def search_stats(self) -> dict:
+        a, b, c, d = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        N.check(self._lib.b200_index_search_stats(self._handle(), C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"groups": a.value, "flagged": b.value, "collect_passes": c.value, "unresolved_async": d.value}
 
     # -- score modifiers -----------------------------------------------------------------------
     def set_attributes(self, column: int, doc_ids: Sequence[int], values: Optional[Sequence[float]]) -> None:
@@ -117,27 +170,19 @@ class RowStore:
                 raise ValueError("values must have one entry per document")
         N.check(self._lib.b200_index_set_attributes(self._handle(), int(column), _ptr(d), _ptr(v), d.shape[0]))
 
+    def set_attributes_multi(self, columns: Sequence[int], doc_ids: Sequence[int], values: Sequence[float]) -> None:
+        """Many (column, document, value) cells in one call."""
+        c, d, v = _as(columns, np.int32), _as(doc_ids, np.int32), _as(values, np.float64)
+        if not (c.shape == d.shape == v.shape):
+            raise ValueError("columns, doc_ids and values must have the same length")
+        N.check(self._lib.b200_index_set_attributes_multi(self._handle(), _ptr(c), _ptr(d), _ptr(v), c.shape[0]))
+
     def search_modified(self, queries, k: int, mult: Sequence[Tuple[int, float]] = (),
                         add: Sequence[Tuple[int, float]] = ()) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         """search() ranked by modify(closeness) = prod(w * attr) * closeness + sum(w * attr)
         (unstructured_vespa_schema.py:266-271).  mult / add: [(attribute column, weight), ...].
         -> (doc, row, modified score)."""
-        q = _as(queries, np.float32)
-        if q.ndim == 1:
-            q = q[None, :]
-        if q.ndim != 2 or q.shape[1] != self.dim:
-            raise ValueError(f"expected [nq, {self.dim}] queries, got {q.shape}")
-        nq = q.shape[0]
-        mc = _as([c for c, _ in mult], np.int32)
-        mw = _as([w for _, w in mult], np.float64)
-        ac = _as([c for c, _ in add], np.int32)
-        aw = _as([w for _, w in add], np.float64)
-        doc = np.empty((nq, k), dtype=np.int32)
-        row = np.empty((nq, k), dtype=np.int32)
-        score = np.empty((nq, k), dtype=np.float64)
-        N.check(self._lib.b200_index_search_modified(self._handle(), _ptr(q), nq, int(k), _ptr(mc), _ptr(mw), len(mc),
-                                                     _ptr(ac), _ptr(aw), len(ac), _ptr(doc), _ptr(row), _ptr(score)))
-        return doc, row, score
+        return self.search(queries, k, mult=mult, add=add)
 
     def search_device(self, d_q_ptr: int, nq: int, k: int, d_doc_ptr: int, d_row_ptr: int, d_score_ptr: int,
                       sync: bool = True) -> None:
@@ -159,6 +204,13 @@ class RowStore:
                                                  C.c_void_p(d_doc_ptr), C.c_void_p(d_row_ptr), C.c_void_p(d_score_ptr),
                                                  1 if sync else 0))
 
+    def search_exchange(self, exchange: "Exchange", d_q_ptr: int, nq: int, k: int, d_block_ptr: int, d_doc_ptr: int,
+                        d_row_ptr: int, d_score_ptr: int, sync: bool = True) -> None:
+        """Local search + fused peer-store exchange + merge (b200_index_search_exchange)."""
+        N.check(self._lib.b200_index_search_exchange(self._handle(), exchange._handle(), C.c_void_p(d_q_ptr), int(nq),
+                                                     int(k), C.c_void_p(d_block_ptr), C.c_void_p(d_doc_ptr),
+                                                     C.c_void_p(d_row_ptr), C.c_void_p(d_score_ptr), 1 if sync else 0))
+
     def last_timing(self) -> Tuple[float, float]:
         a, b = C.c_float(0), C.c_float(0)
         N.check(self._lib.b200_index_last_timing(self._handle(), C.byref(a), C.byref(b)))
@@ -177,6 +229,43 @@ class RowStore:
         N.check(lib.b200_index_info(h, C.byref(d), C.byref(m), C.byref(dev)))
         names = {v: k for k, v in _METRICS.items()}
         return cls(dim=d.value, metric=names[m.value], device=dev.value, _handle=h)
+
+
+class Exchange:
+    """Symmetric NVLink exchange buffer of one rank (b200_exchange_*).  `handle` (64 bytes) is what the ranks swap;
+    `open(all_handles)` maps the peers' buffers."""
+
+    def __init__(self, device: int, rank: int, world: int, max_nq: int = 64, max_k: int = 16):
+        self._lib = N.load()
+        h = C.c_void_p()
+        buf = (C.c_uint8 * N.EXCHANGE_HANDLE_BYTES)()
+        N.check(self._lib.b200_exchange_create(int(device), int(rank), int(world), int(max_nq), int(max_k), C.byref(h),
+                                               C.cast(buf, C.c_void_p)))
+        self._h = h
+        self.rank, self.world = int(rank), int(world)
+        self.handle = bytes(buf)
+
+    def open(self, handles: Sequence[bytes]) -> None:
+        if len(handles) != self.world or any(len(h) != N.EXCHANGE_HANDLE_BYTES for h in handles):
+            raise ValueError("expected one 64-byte handle per rank")
+        blob = b"".join(handles)
+        N.check(self._lib.b200_exchange_open(self._handle(), C.c_char_p(blob)))
+
+    def _handle(self):
+        if not self._h:
+            raise RuntimeError("Exchange is closed")
+        return self._h
+
+    def close(self) -> None:
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.b200_exchange_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def topk_merge(doc: np.ndarray, row: np.ndarray, score: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

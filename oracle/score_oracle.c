@@ -22,9 +22,19 @@
  * oracle DEFINES the total order (score desc, doc id asc) — "tie order: defined here, not pinned".
  *
  * Storage contract shared with the CUDA path: rows are fp16 (BASELINE.json configs[4]); the score is the
- * fp64 dot product of the fp16-rounded operands accumulated in the fixed order
- *     partial[l] = sum_{j ascending} q[32 j + l] * c[32 j + l]   (l = 0..31),   dot = sum_{l ascending} partial[l]
- * (every product of two fp16 values is exact in fp64).
+ * fp64 dot product of the fp16-rounded operands accumulated in the fixed order (one warp of the CUDA path, 16-byte
+ * loads per lane):
+ *     partial[l] = sum over j ascending, then t = 0..7, of q[i] * c[i] with i = 256 j + 8 l + t   (l = 0..31)
+ *     dot        = xor-butterfly of the partials: for o in 16, 8, 4, 2, 1: partial[l] += partial[l ^ o]
+ * (every product of two fp16 values is exact in fp64, so fused / unfused multiply-add agree; IEEE addition is
+ * commutative, so every lane of the butterfly ends with the same bits).
+ *
+ * TOTAL ORDER (defined here; the CUDA path proves it reproduces it — score.cu header, "GUARD"):
+ *   per document: best row = max exact dot, ties -> lowest row;  across documents: (key desc, doc id asc), where
+ *   key = exact dot (or minus squared distance, or the modified score).  The CUDA path selects candidates with an
+ *   approximate tensor-core key but only returns a result after checking, per query, that the exact key of the k-th
+ *   document exceeds (bound of every unexamined row's approximate key) + (bound of the approximation error);
+ *   otherwise it re-collects every row above a safe threshold and re-scores all of them.
  */
 #include <math.h>
 #include <stdint.h>
@@ -110,28 +120,40 @@ void oracle_convert_rows(const float* src, uint16_t* dst, int64_t rows, int dim,
 }
 
 /* operands pre-widened to fp32 (exact); same summation order as documented above */
+static double butterfly32(double* part) {
+    for (int o = 16; o > 0; o >>= 1) {
+        double nxt[32];
+        for (int l = 0; l < 32; ++l) nxt[l] = part[l] + part[l ^ o];
+        memcpy(part, nxt, sizeof(nxt));
+    }
+    return part[0];
+}
+
 static double exact_dot_f(const float* q, const float* c, int dim) {
     double part[32];
-    for (int l = 0; l < 32; ++l) part[l] = 0.0;
-    for (int i = 0; i < dim; i += 32)
-        for (int l = 0; l < 32 && i + l < dim; ++l) part[l] += (double)q[i + l] * (double)c[i + l];
-    double tot = 0.0;
-    for (int l = 0; l < 32; ++l) tot += part[l];
-    return tot;
+    for (int l = 0; l < 32; ++l) {
+        double p = 0.0;
+        for (int base = 8 * l; base < dim; base += 256)
+            for (int t = 0; t < 8; ++t) p += (double)q[base + t] * (double)c[base + t];
+        part[l] = p;
+    }
+    return butterfly32(part);
 }
 
 /* euclidean: the ordering key is minus the squared distance, sum of exact (q - c)^2 terms in the same fixed order */
 static double exact_neg_sqdist_f(const float* q, const float* c, int dim) {
     double part[32];
-    for (int l = 0; l < 32; ++l) part[l] = 0.0;
-    for (int i = 0; i < dim; i += 32)
-        for (int l = 0; l < 32 && i + l < dim; ++l) {
-            double d = (double)q[i + l] - (double)c[i + l];
-            part[l] -= d * d;
-        }
-    double tot = 0.0;
-    for (int l = 0; l < 32; ++l) tot += part[l];
-    return tot;
+    for (int l = 0; l < 32; ++l) {
+        double p = 0.0;
+        for (int base = 8 * l; base < dim; base += 256)
+            for (int t = 0; t < 8; ++t) {
+                double d = (double)q[base + t] - (double)c[base + t];
+                volatile double sq = d * d;   /* unfused, like __dmul_rn / __dsub_rn */
+                p = p - sq;
+            }
+        part[l] = p;
+    }
+    return butterfly32(part);
 }
 
 double oracle_closeness(double dot, int metric) {
