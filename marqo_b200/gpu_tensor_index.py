@@ -22,6 +22,8 @@ from __future__ import annotations
 import math
 import re
 import threading
+import time
+from collections import OrderedDict
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -103,6 +105,31 @@ def _wrap(kind: str, js: dict):
         return _Obj(responses=resp, errors=js["errors"])
 
 
+class DeviceChunks:
+    """Embeddings of one tensor field of one document that are ALREADY on the index's GPU (fp32 [n, dim], row-major):
+    what the add_documents fast path puts in `fields['marqo__embeddings_<f>']` instead of {"0": [floats], ...}
+    (semi_structured_document.py:139-141) so the vectors never visit the host.  `owner` keeps the device buffer alive
+    (a torch tensor, or anything else) until feed_batch has copied the rows into the row store."""
+
+    __slots__ = ("keys", "ptr", "dim", "owner")
+
+    def __init__(self, keys: List[str], ptr: int, dim: int, owner=None):
+        self.keys = [str(k) for k in keys]
+        self.ptr = int(ptr)
+        self.dim = int(dim)
+        self.owner = owner
+
+
+class _FilterEntry:
+    __slots__ = ("keep", "bits", "tag", "packed")
+
+    def __init__(self, keep):
+        self.keep = keep
+        self.bits = np.zeros(0, dtype=bool)    # per document number: may match
+        self.tag = 0
+        self.packed = None                     # uint32 bitset of `bits`, rebuilt lazily
+
+
 class _Schema:
     def __init__(self):
         self.stores: Dict[str, RowStore] = {}          # embeddings field -> row store
@@ -113,17 +140,95 @@ class _Schema:
         self.doc_rows: List[Dict[str, List[int]]] = [] # document number -> field -> rows
         self.attr_col: Dict[str, int] = {}             # score-modifier attribute name -> device column
         self.attrs: List[Dict[str, float]] = []        # document number -> its marqo__score_modifiers cells
+        self.dead: Dict[str, int] = {}                 # embeddings field -> tombstoned rows still in the matrix
+        self.epoch = 0                                 # bumped when row numbers change (compaction)
+        self.filters: "OrderedDict[str, _FilterEntry]" = OrderedDict()   # filter text -> document bitset (LRU)
+        self.n_live = 0
+
+
+class _Batch:
+    __slots__ = ("queries", "ks", "done", "result", "error", "closed")
+
+    def __init__(self):
+        self.queries: List[np.ndarray] = []
+        self.ks: List[int] = []
+        self.done = threading.Event()
+        self.result = None
+        self.error = None
+        self.closed = False
+
+
+class _Coalescer:
+    """Gathers concurrent single-query searches into one scan.  Marqo issues one `vespa_client.query()` per request
+    (tensor_search.py:2189) from up to 8 concurrent search threads (api/configs.py:27-28); a corpus scan costs the same
+    for 1 or 64 queries (the kernel is HBM-bound), so requests that arrive within a short window and agree on
+    (row store, modifiers, filter) share a scan.  The first arrival leads: it waits `window_s` only when other requests
+    are in flight, closes the batch, runs it, and hands every follower its slice."""
+
+    def __init__(self, window_s: float = 0.0002, max_batch: int = 64):
+        self.window_s = window_s
+        self.max_batch = max_batch
+        self._lock = threading.Lock()
+        self._open: Dict[Any, _Batch] = {}
+        self.active = 0            # requests currently inside GpuTensorIndex.query()
+        self.batches = 0
+        self.queries = 0
+
+    def submit(self, key, q: np.ndarray, k: int, run):
+        """run(Q [n, dim], kmax) -> (doc, row, score) arrays [n, kmax].  Returns this query's ([k], [k], [k])."""
+        with self._lock:
+            b = self._open.get(key)
+            leader = b is None or b.closed or len(b.queries) >= self.max_batch
+            if leader:
+                b = _Batch()
+                self._open[key] = b
+            slot = len(b.queries)
+            b.queries.append(q)
+            b.ks.append(k)
+            others = self.active > 1
+        if not leader:
+            b.done.wait()
+            if b.error is not None:
+                raise b.error
+        else:
+            if others and self.window_s > 0:
+                deadline = time.perf_counter() + self.window_s
+                while time.perf_counter() < deadline and len(b.queries) < self.max_batch:
+                    time.sleep(self.window_s / 4)
+            with self._lock:
+                b.closed = True
+                if self._open.get(key) is b:
+                    del self._open[key]
+                Q = np.stack(b.queries)
+                kmax = max(b.ks)
+                self.batches += 1
+                self.queries += len(b.queries)
+            try:
+                b.result = run(Q, kmax)
+            except BaseException as e:   # followers must not hang
+                b.error = e
+                b.done.set()
+                raise
+            b.done.set()
+        doc, row, score = b.result
+        return doc[slot, :k], row[slot, :k], score[slot, :k]
 
 
 class GpuTensorIndex:
+    COMPACT_MIN_DEAD = 4096        # compaction threshold: dead rows >= this AND >= COMPACT_DEAD_FRACTION of the matrix
+    COMPACT_DEAD_FRACTION = 0.3
+    MAX_CACHED_FILTERS = 32
+
     def __init__(self, metric: str = "prenormalized-angular", device: int = 0, delegate=None,
-                 default_search_timeout_ms: int = 1000):
+                 default_search_timeout_ms: int = 1000, coalesce_window_s: float = 0.0002):
         self.metric = metric
         self.device = device
         self.delegate = delegate
         self.default_search_timeout_ms = default_search_timeout_ms
         self._schemas: Dict[str, _Schema] = {}
         self._lock = threading.RLock()
+        self._coalescer = _Coalescer(window_s=coalesce_window_s)
+        self._next_tag = 1
 
     def close(self) -> None:
         with self._lock:
@@ -132,6 +237,9 @@ class GpuTensorIndex:
                     st.close()
             self._schemas.clear()
 
+    def coalescer_stats(self) -> Dict[str, int]:
+        return {"batches": self._coalescer.batches, "queries": self._coalescer.queries}
+
     # ------------------------------------------------------------------------------------------------ feed
     @staticmethod
     def _doc_id_and_fields(doc) -> Tuple[str, dict]:
@@ -139,103 +247,315 @@ class GpuTensorIndex:
             return doc["id"], doc["fields"]
         return doc.id, doc.fields
 
-    def _tombstone(self, s: _Schema, num: int) -> None:
-        for f, rows in s.doc_rows[num].items():
-            if rows:
-                s.stores[f].delete_doc(num)
-        s.doc_rows[num] = {}
-        if s.attrs[num]:
-            for store in s.stores.values():
-                store.set_attributes(-1, [num], None)
-            s.attrs[num] = {}
-
     @staticmethod
     def _replay_attributes(s: _Schema, store: RowStore) -> None:
         """A row store created after documents were fed (a new tensor field) gets their attribute cells."""
-        by_col: Dict[int, Tuple[List[int], List[float]]] = {}
+        cols, ids, vals = [], [], []
         for num, attrs in enumerate(s.attrs):
             for name, v in attrs.items():
-                ids, vals = by_col.setdefault(s.attr_col[name], ([], []))
+                cols.append(s.attr_col[name])
                 ids.append(num)
                 vals.append(v)
-        for col, (ids, vals) in by_col.items():
-            store.set_attributes(col, ids, vals)
+        if cols:
+            store.set_attributes_multi(cols, ids, vals)
+
+    def _fp16_limit(self) -> Optional[float]:
+        # the angular metric L2-normalises rows at insert time: any finite vector fits; the others store values as given
+        return None if self.metric == "angular" else 65504.0
+
+    def _parse_document(self, s: _Schema, fields: dict, pending_cols: Dict[str, int]):
+        """Everything that can reject a document, with NO side effect on the schema: -> (staged {field: (keys, mat |
+        DeviceChunks)}, attrs).  Raises ValueError / KeyError / TypeError with the message for the 400 response."""
+        staged = {}
+        limit = self._fp16_limit()
+        for f, cells in fields.items():
+            if not f.startswith(EMBEDDINGS_PREFIX):
+                continue
+            if isinstance(cells, DeviceChunks):
+                dim, keys, mat = cells.dim, cells.keys, cells
+            else:
+                if not isinstance(cells, dict):
+                    raise ValueError(f"field {f}: expected a mapped tensor {{chunk: [floats]}}")
+                keys = [str(k) for k in cells.keys()]
+                mat = np.asarray([cells[k] for k in cells.keys()], dtype=np.float32)
+                if mat.size and mat.ndim != 2:
+                    raise ValueError(f"field {f}: ragged embeddings")
+                if not len(keys):
+                    continue
+                if not np.isfinite(mat).all():
+                    raise ValueError(f"field {f}: embedding values must be finite")
+                if limit is not None and np.abs(mat).max() > limit:
+                    raise ValueError(f"field {f}: embedding values beyond +-{limit:g} do not fit the fp16 row store")
+                dim = mat.shape[1]
+            store = s.stores.get(f)
+            if store is not None and dim != store.dim:
+                raise ValueError(f"field {f}: embedding dimension {dim} != index dimension {store.dim}")
+            if store is None and (dim <= 0 or dim % 64 != 0 or dim > 1024):
+                raise ValueError(f"field {f}: embedding dimension {dim} is not a multiple of 64 in [64, 1024]")
+            staged[f] = (keys, mat)
+        attrs: Dict[str, float] = {}
+        for tensor_field in SCORE_MODIFIER_FIELDS:
+            cells = fields.get(tensor_field) or {}
+            if isinstance(cells, dict) and "cells" in cells and isinstance(cells["cells"], (dict, list)):
+                cells = cells["cells"]          # Vespa's verbose tensor JSON form
+            if isinstance(cells, list):
+                cells = {c["address"]["p"]: c["value"] for c in cells}
+            for name, v in cells.items():
+                # structured indexes keep float-typed modifier fields in a tensor<float>: fp32 cells
+                attrs[str(name)] = float(np.float32(v)) if tensor_field.endswith("_float") else float(v)
+        new_cols = 0
+        for name, v in attrs.items():
+            if not math.isfinite(v):
+                raise ValueError(f"score modifier field {name}: value {v} is not finite")
+            if name not in s.attr_col and name not in pending_cols:
+                new_cols += 1
+        if len(s.attr_col) + len(pending_cols) + new_cols > MAX_ATTRIBUTE_COLUMNS:
+            raise ValueError(f"more than {MAX_ATTRIBUTE_COLUMNS} distinct score-modifier fields")
+        return staged, attrs
 
     def feed_batch(self, batch: List[Any], schema: str, concurrency: Optional[int] = None, timeout: int = 60):
         """vespa_client.py:267-296.  Embeddings arrive as fields['marqo__embeddings[_<field>]'] = {"0": [...], ...}
-        (semi_structured_document.py:139-141; unstructured_add_document_handler.py:162-163)."""
-        responses = []
+        (semi_structured_document.py:139-141; unstructured_add_document_handler.py:162-163) or, on the device fast
+        path, as DeviceChunks.
+
+        Two phases.  (1) every document is parsed and validated with no side effect; a rejected document gets its 400
+        and leaves the index exactly as it was (Vespa leaves the old version of a failed put intact).  (2) the accepted
+        documents are committed with ONE row append per tensor field, ONE tombstone scatter per field for the replaced
+        versions and ONE attribute scatter per row store — no per-document device allocation or synchronisation.  A
+        native failure in phase 2 (out of device memory, ...) undoes the host-side registration of the whole batch and
+        is reported per document as a 507."""
+        responses: List[Optional[dict]] = [None] * len(batch)
         errors = False
         with self._lock:
             s = self._schemas.setdefault(schema, _Schema())
-            for doc in batch:
-                doc_id, fields = self._doc_id_and_fields(doc)
-                path_id = f"/document/v1/{schema}/{schema}/docid/{doc_id}"
-                full_id = f"id:{schema}:{schema}::{doc_id}"
+            accepted = []            # (position, doc_id, fields, staged, attrs) in feed order
+            pending_cols: Dict[str, int] = {}
+            for pos, doc in enumerate(batch):
+                doc_id, fields = None, None
                 try:
-                    emb_fields = {k: v for k, v in fields.items() if k.startswith(EMBEDDINGS_PREFIX)}
-                    staged = {}
-                    for f, cells in emb_fields.items():
-                        if not isinstance(cells, dict):
-                            raise ValueError(f"field {f}: expected a mapped tensor {{chunk: [floats]}}")
-                        keys = list(cells.keys())
-                        mat = np.asarray([cells[k] for k in keys], dtype=np.float32)
-                        if mat.size and mat.ndim != 2:
-                            raise ValueError(f"field {f}: ragged embeddings")
-                        staged[f] = (keys, mat)
-                    attrs: Dict[str, float] = {}
-                    for tensor_field in SCORE_MODIFIER_FIELDS:
-                        cells = fields.get(tensor_field) or {}
-                        if isinstance(cells, dict) and "cells" in cells and isinstance(cells["cells"], (dict, list)):
-                            cells = cells["cells"]          # Vespa's verbose tensor JSON form
-                        if isinstance(cells, list):
-                            cells = {c["address"]["p"]: c["value"] for c in cells}
-                        for name, v in cells.items():
-                            # structured indexes keep float-typed modifier fields in a tensor<float>: fp32 cells
-                            attrs[str(name)] = float(np.float32(v)) if tensor_field.endswith("_float") else float(v)
-                    for name, v in attrs.items():
-                        if not math.isfinite(v):
-                            raise ValueError(f"score modifier field {name}: value {v} is not finite")
-                        if name not in s.attr_col:
-                            if len(s.attr_col) >= MAX_ATTRIBUTE_COLUMNS - 1:     # the last column is the filter mask
-                                raise ValueError(f"more than {MAX_ATTRIBUTE_COLUMNS - 1} distinct score-modifier fields")
-                            s.attr_col[name] = len(s.attr_col)
-                    num = s.doc_num.get(doc_id)
-                    if num is None:
-                        num = len(s.doc_ids)
-                        s.doc_num[doc_id] = num
-                        s.doc_ids.append(doc_id)
-                        s.fields.append(None)
-                        s.doc_rows.append({})
-                        s.attrs.append({})
-                    else:
-                        self._tombstone(s, num)          # add_documents replaces by _id
-                        s.doc_ids[num] = doc_id
-                    for f, (keys, mat) in staged.items():
-                        if not len(keys):
-                            continue
-                        store = s.stores.get(f)
-                        if store is None:
-                            store = RowStore(mat.shape[1], metric=self.metric, device=self.device)
-                            s.stores[f] = store
-                            s.row_chunk[f] = []
-                            self._replay_attributes(s, store)
-                        if mat.shape[1] != store.dim:
-                            raise ValueError(f"field {f}: embedding dimension {mat.shape[1]} != index dimension {store.dim}")
-                        row0 = len(store)
-                        store.add(mat, np.full(len(keys), num, dtype=np.int32))
-                        s.row_chunk[f].extend((num, k) for k in keys)
-                        s.doc_rows[num][f] = list(range(row0, row0 + len(keys)))
-                    s.fields[num] = {k: v for k, v in fields.items() if not k.startswith(EMBEDDINGS_PREFIX)}
-                    s.attrs[num] = attrs
-                    for store in s.stores.values():
-                        for name, v in attrs.items():
-                            store.set_attributes(s.attr_col[name], [num], [v])
-                    responses.append({"status": 200, "pathId": path_id, "id": full_id, "message": None})
-                except (ValueError, KeyError, TypeError) as e:
+                    doc_id, fields = self._doc_id_and_fields(doc)
+                    staged, attrs = self._parse_document(s, fields, pending_cols)
+                    for name in attrs:
+                        if name not in s.attr_col and name not in pending_cols:
+                            pending_cols[name] = len(s.attr_col) + len(pending_cols)
+                    accepted.append((pos, doc_id, fields, staged, attrs))
+                except (ValueError, KeyError, TypeError, AttributeError) as e:
                     errors = True
-                    responses.append({"status": 400, "pathId": path_id, "id": full_id, "message": str(e)})
+                    responses[pos] = {"status": 400, "pathId": f"/document/v1/{schema}/{schema}/docid/{doc_id}",
+                                      "id": f"id:{schema}:{schema}::{doc_id}", "message": str(e)}
+            # the LAST put of an id within the batch wins (Vespa applies puts in order); earlier ones succeed and vanish
+            last_pos = {doc_id: pos for pos, doc_id, *_ in accepted}
+            undo = self._commit(s, schema, [a for a in accepted if last_pos[a[1]] == a[0]], pending_cols)
+            for pos, doc_id, *_ in accepted:
+                status, msg = (200, None) if undo is None else (507, undo)
+                errors = errors or undo is not None
+                responses[pos] = {"status": status, "pathId": f"/document/v1/{schema}/{schema}/docid/{doc_id}",
+                                  "id": f"id:{schema}:{schema}::{doc_id}", "message": msg}
         return _wrap("FeedBatchResponse", {"responses": responses, "errors": errors})
+
+    def _commit(self, s: _Schema, schema: str, docs, pending_cols: Dict[str, int]) -> Optional[str]:
+        """Phase 2 of feed_batch.  Returns None on success, else the failure text (the index is unchanged then, except
+        for appended-but-tombstoned rows)."""
+        if not docs:
+            return None
+        n_before = len(s.doc_ids)
+        new_ids: List[str] = []
+        nums: List[int] = []
+        for _, doc_id, *_ in docs:
+            num = s.doc_num.get(doc_id)
+            if num is None:
+                num = n_before + len(new_ids)
+                new_ids.append(doc_id)
+            nums.append(num)
+        replaced = [n for n in nums if n < n_before]
+        # ---- device work first; host maps are only touched once it has all succeeded
+        appended: Dict[str, Tuple[int, int]] = {}        # field -> (first new row, count)
+        created: List[str] = []
+        try:
+            per_field: Dict[str, list] = {}
+            for (_, _, _, staged, _), num in zip(docs, nums):
+                for f, (keys, mat) in staged.items():
+                    per_field.setdefault(f, []).append((num, keys, mat))
+            for f, items in per_field.items():
+                store = s.stores.get(f)
+                if store is None:
+                    dim = items[0][2].dim if isinstance(items[0][2], DeviceChunks) else items[0][2].shape[1]
+                    for _, _, m in items:
+                        d = m.dim if isinstance(m, DeviceChunks) else m.shape[1]
+                        if d != dim:
+                            raise ValueError(f"field {f}: embedding dimension {d} != index dimension {dim}")
+                    store = RowStore(dim, metric=self.metric, device=self.device)
+                    s.stores[f] = store
+                    s.row_chunk[f] = []
+                    s.dead[f] = 0
+                    created.append(f)
+                    self._replay_attributes(s, store)
+                row0 = len(store)
+                host_rows, host_ids = [], []
+                dev_ptr, dev_ids = 0, []      # a run of DeviceChunks that are contiguous in device memory
+
+                def flush_host():
+                    nonlocal host_rows, host_ids
+                    if host_rows:
+                        store.add(np.concatenate(host_rows), np.concatenate(host_ids))
+                        host_rows, host_ids = [], []
+
+                def flush_dev():
+                    nonlocal dev_ptr, dev_ids
+                    if dev_ids:
+                        store.add_device_docs(dev_ptr, np.asarray(dev_ids, dtype=np.int32))
+                        dev_ptr, dev_ids = 0, []
+
+                for num, keys, mat in items:       # rows are appended in feed order
+                    if isinstance(mat, DeviceChunks):
+                        flush_host()
+                        if dev_ids and mat.ptr != dev_ptr + len(dev_ids) * store.dim * 4:
+                            flush_dev()
+                        if not dev_ids:
+                            dev_ptr = mat.ptr
+                        dev_ids.extend([num] * len(keys))      # the vectoriser hands out consecutive slices of one
+                    else:                                      # tensor: a whole batch becomes ONE device append
+                        flush_dev()
+                        host_rows.append(mat)
+                        host_ids.append(np.full(len(keys), num, dtype=np.int32))
+                flush_host()
+                flush_dev()
+                appended[f] = (row0, len(store) - row0)
+            # attribute cells: clear the replaced documents' old cells, then write the new ones (per row store)
+            cols, ids, vals = [], [], []
+            col_of = dict(s.attr_col)
+            col_of.update(pending_cols)
+            for (_, _, _, _, attrs), num in zip(docs, nums):
+                for name, v in attrs.items():
+                    cols.append(col_of[name])
+                    ids.append(num)
+                    vals.append(v)
+            had_attrs = [n for n in replaced if s.attrs[n]]
+            for store in s.stores.values():
+                if had_attrs:
+                    store.set_attributes(-1, had_attrs, None)
+                if cols:
+                    store.set_attributes_multi(cols, ids, vals)
+            # tombstone the replaced versions' rows (all fields), one scatter per field
+            for f, store in s.stores.items():
+                old = [r for n in replaced for r in s.doc_rows[n].get(f, ())]
+                if old:
+                    store.delete_rows(old)
+                    s.dead[f] = s.dead.get(f, 0) + len(old)
+        except (NativeError, ValueError) as e:
+            # undo: rows appended by this batch become tombstones; nothing else was changed on the host.  (Attribute
+            # cells of replaced documents may have been rewritten: restore them from the host copy.)
+            for f, (row0, cnt) in appended.items():
+                try:
+                    if cnt:
+                        s.stores[f].delete_rows(np.arange(row0, row0 + cnt, dtype=np.int32))
+                        s.row_chunk[f].extend((-1, "") for _ in range(cnt))
+                        s.dead[f] = s.dead.get(f, 0) + cnt
+                except NativeError:
+                    pass
+            for f in created:
+                if f not in appended:
+                    s.stores.pop(f).close()
+                    s.row_chunk.pop(f, None)
+            try:
+                rc, ri, rv = [], [], []
+                for n in replaced:
+                    for name, v in s.attrs[n].items():
+                        rc.append(s.attr_col[name]); ri.append(n); rv.append(v)
+                for store in s.stores.values():
+                    if replaced:
+                        store.set_attributes(-1, replaced, None)
+                    if rc:
+                        store.set_attributes_multi(rc, ri, rv)
+            except NativeError:
+                pass
+            return str(getattr(e, "message", e))
+        # ---- host registration (cannot fail)
+        s.attr_col.update(pending_cols)
+        for doc_id in new_ids:
+            s.doc_num[doc_id] = len(s.doc_ids)
+            s.doc_ids.append(doc_id)
+            s.fields.append(None)
+            s.doc_rows.append({})
+            s.attrs.append({})
+        s.n_live += len(new_ids)
+        for n in replaced:
+            s.doc_rows[n] = {}
+        cursor = {f: row0 for f, (row0, _) in appended.items()}
+        for (_, doc_id, fields, staged, attrs), num in zip(docs, nums):
+            s.doc_ids[num] = doc_id
+            for f, (keys, _) in staged.items():
+                r0 = cursor[f]
+                s.row_chunk[f].extend((num, k) for k in keys)
+                s.doc_rows[num][f] = list(range(r0, r0 + len(keys)))
+                cursor[f] = r0 + len(keys)
+            s.fields[num] = {k: v for k, v in fields.items() if not k.startswith(EMBEDDINGS_PREFIX)}
+            s.attrs[num] = attrs
+        self._filters_update(s, nums)
+        self._maybe_compact(s)
+        return None
+
+    def _maybe_compact(self, s: _Schema) -> None:
+        """Tombstoned rows are squeezed out once they are a sizeable share of a matrix (update-heavy feeds would
+        otherwise grow HBM use and scan time without bound)."""
+        for f, store in s.stores.items():
+            dead = s.dead.get(f, 0)
+            rows = len(s.row_chunk[f])
+            if dead < self.COMPACT_MIN_DEAD or dead < self.COMPACT_DEAD_FRACTION * rows:
+                continue
+            new_of_old = store.compact()
+            rc = s.row_chunk[f]
+            s.row_chunk[f] = [rc[i] for i in np.flatnonzero(new_of_old >= 0)]
+            for num in range(len(s.doc_rows)):
+                rows_f = s.doc_rows[num].get(f)
+                if rows_f:
+                    s.doc_rows[num][f] = [int(new_of_old[r]) for r in rows_f]
+            s.dead[f] = 0
+            s.epoch += 1
+
+    # ------------------------------------------------------------------------------------------------ filters
+    def _filter_entry(self, s: _Schema, text: str) -> _FilterEntry:
+        """The document bitset of one filter string: compiled and evaluated over the schema ONCE, then kept current by
+        feed_batch / delete_batch (only the touched documents are re-evaluated)."""
+        e = s.filters.get(text)
+        if e is None:
+            e = _FilterEntry(compile_filter(text))
+            n = len(s.doc_ids)
+            e.bits = np.fromiter((d is not None and bool(e.keep(s.fields[i] or {})) for i, d in enumerate(s.doc_ids)),
+                                 dtype=bool, count=n)
+            e.tag = self._take_tag()
+            s.filters[text] = e
+            while len(s.filters) > self.MAX_CACHED_FILTERS:
+                s.filters.popitem(last=False)
+        else:
+            s.filters.move_to_end(text)
+        return e
+
+    def _take_tag(self) -> int:
+        self._next_tag += 1
+        return self._next_tag
+
+    def _filters_update(self, s: _Schema, nums: List[int]) -> None:
+        if not s.filters or not nums:
+            return
+        n = len(s.doc_ids)
+        for e in s.filters.values():
+            if len(e.bits) < n:
+                e.bits = np.concatenate([e.bits, np.zeros(n - len(e.bits), dtype=bool)])
+            for num in nums:
+                e.bits[num] = s.doc_ids[num] is not None and bool(e.keep(s.fields[num] or {}))
+            e.tag = self._take_tag()
+            e.packed = None
+
+    @staticmethod
+    def _packed(e: _FilterEntry) -> np.ndarray:
+        if e.packed is None:
+            b = np.packbits(e.bits, bitorder="little")
+            pad = (-len(b)) % 4
+            if pad:
+                b = np.concatenate([b, np.zeros(pad, np.uint8)])
+            e.packed = b.view(np.uint32) if len(b) else np.zeros(1, np.uint32)
+        return e.packed
 
     # ------------------------------------------------------------------------------------------------ query
     @staticmethod
@@ -302,14 +622,15 @@ class GpuTensorIndex:
         for k in ADD_WEIGHTS_INPUTS:
             add.update(self._weights(query_features.get(k)))
         filter_text = self._split_where(yql)[1]
-        keep = compile_filter(filter_text) if filter_text is not None else None
-        with self._lock:
+        co = self._coalescer
+        with co._lock:
+            co.active += 1
+        try:
             s = self._schemas.get(schema)
             children, n_docs = [], 0
             if s is not None:
-                n_docs = sum(1 for d in s.doc_ids if d is not None)
                 try:
-                    children = self._search(s, schema, fields, q, hits, offset, mult, add, keep)
+                    children, n_docs = self._search(s, schema, fields, q, hits, offset, mult, add, filter_text)
                 except NativeError as e:
                     if e.code != ERR_UNSUPPORTED:
                         raise
@@ -317,6 +638,9 @@ class GpuTensorIndex:
                         return self.delegate.query(yql, hits=hits, ranking=ranking, model_restrict=model_restrict,
                                                    query_features=query_features, timeout=timeout, **kwargs)
                     raise VespaError(f"GpuTensorIndex cannot answer this query: {e.message}") from e
+        finally:
+            with co._lock:
+                co.active -= 1
         js = {"root": {"id": "toplevel", "relevance": 1.0, "fields": {"totalCount": len(children) + offset},
                        "coverage": {"coverage": 100, "documents": n_docs, "full": True, "nodes": 1, "results": 1,
                                     "resultsFull": 1},
@@ -351,56 +675,57 @@ class GpuTensorIndex:
                 a += w * attrs[name]
         return m, a
 
-    MAX_FETCH = 10000   # b200_index_search's own k limit (Marqo's limit + offset cap, tensor_search.py:1568-1588)
+    MAX_FETCH = 11000   # b200_index_search's own k limit (Marqo's limit + offset cap, api/configs.py:24-25)
 
     def _search(self, s: _Schema, schema: str, fields: List[str], q: np.ndarray, hits: int, offset: int,
                 mult: Optional[Dict[str, float]] = None, add: Optional[Dict[str, float]] = None,
-                keep=None) -> List[dict]:
+                filter_text: Optional[str] = None) -> Tuple[List[dict], int]:
         k = hits + offset
         if k <= 0:
-            return []
-        # a weight on an attribute no document has multiplies / adds nothing anywhere: drop the term
-        mult_cols = [(s.attr_col[n], w) for n, w in (mult or {}).items() if n in s.attr_col]
-        add_cols = [(s.attr_col[n], w) for n, w in (add or {}).items() if n in s.attr_col]
-        modified = bool(mult_cols) or bool(add_cols)
-        verdict: Dict[int, bool] = {}
-
-        def allowed(num: int) -> bool:
-            if num not in verdict:
-                verdict[num] = bool(keep(s.fields[num] or {}))
-            return verdict[num]
-
-        best: Dict[int, Tuple[float, str, int]] = {}   # doc number -> (score, field, row)
-        for f in fields:
-            store = s.stores.get(f)
-            if store is None or len(store) == 0:
-                continue
-            if q.shape[-1] != store.dim:
-                raise VespaStatusError(400, f"Expected a tensor of dimension {store.dim} for query input but got "
-                                            f"{q.shape[-1]}")
-            # A filter is evaluated on the host against the stored fields; the exact top-k of the ALLOWED documents is
-            # the first k allowed entries of the unfiltered ranking, so fetch deeper until k of them have been seen.
-            fetch = k
-            while True:
-                if modified:
-                    doc, row, score = store.search_modified(q[None, :], fetch, mult_cols, add_cols)
-                else:
-                    doc, row, score = store.search(q[None, :], fetch)
-                found = [(int(d), int(r), float(sc)) for d, r, sc in zip(doc[0], row[0], score[0]) if d >= 0]
-                if keep is not None:
-                    kept = [h for h in found if allowed(h[0])]
-                    exhausted = len(found) < fetch
-                    if len(kept) < k and not exhausted:
-                        if fetch >= self.MAX_FETCH:
-                            # a very selective filter: evaluate it over the whole schema once and let the scan skip
-                            # the excluded documents (one pass instead of ever deeper fetches)
-                            found = self._masked_search(s, store, q, k, allowed, mult_cols, add_cols)
-                            break
-                        fetch = min(self.MAX_FETCH, fetch * 4)
+            return [], s.n_live
+        if k > self.MAX_FETCH:
+            raise VespaStatusError(400, f"hits + offset = {k} exceeds {self.MAX_FETCH}")
+        for attempt in range(4):
+            found: Dict[str, tuple] = {}
+            epoch = None
+            for f in fields:
+                with self._lock:
+                    store = s.stores.get(f)
+                    if store is None or len(store) == 0:
                         continue
-                    found = kept[:k]
-                break
-            for d, r, sc in found:
+                    if q.shape[-1] != store.dim:
+                        raise VespaStatusError(400, f"Expected a tensor of dimension {store.dim} for query input but "
+                                                    f"got {q.shape[-1]}")
+                    if epoch is None:
+                        epoch = s.epoch
+                    # a weight on an attribute no document has multiplies / adds nothing anywhere: drop the term
+                    mult_cols = tuple((s.attr_col[n], w) for n, w in (mult or {}).items() if n in s.attr_col)
+                    add_cols = tuple((s.attr_col[n], w) for n, w in (add or {}).items() if n in s.attr_col)
+
+                def run(Q, kmax, store=store, mult_cols=mult_cols, add_cols=add_cols):
+                    # the leader of a batch runs the scan for everybody, under the index lock (no concurrent mutation)
+                    with self._lock:
+                        kw = {}
+                        if filter_text is not None:
+                            e = self._filter_entry(s, filter_text)
+                            kw = dict(filter_bits=self._packed(e), filter_docs=len(e.bits), filter_tag=e.tag)
+                        return store.search(Q, kmax, mult=mult_cols, add=add_cols, **kw)
+
+                key = (id(store), mult_cols, add_cols, filter_text)
+                found[f] = self._coalescer.submit(key, q, k, run)
+            with self._lock:
+                if epoch is not None and epoch != s.epoch:
+                    continue      # a compaction renumbered rows between the scan and now: search again
+                return self._children(s, schema, found, hits, offset, mult, add), s.n_live
+        raise VespaError("the index kept changing under the query")
+
+    def _children(self, s: _Schema, schema: str, found: Dict[str, tuple], hits: int, offset: int, mult, add) -> List[dict]:
+        modified = bool(mult) or bool(add)
+        best: Dict[int, Tuple[float, str, int]] = {}   # doc number -> (score, field, row)
+        for f, (doc, row, score) in found.items():
+            for d, r, sc in zip(doc.tolist(), row.tolist(), score.tolist()):
+                if d < 0:
+                    continue
                 cur = best.get(d)
                 if cur is None or sc > cur[0]:
                     best[d] = (sc, f, r)
@@ -420,27 +745,6 @@ class GpuTensorIndex:
             children.append({"id": f"id:{schema}:{schema}::{s.doc_ids[num]}", "relevance": sc, "source": "content_default",
                              "fields": out_fields})
         return children
-
-    MASK_COLUMN = MAX_ATTRIBUTE_COLUMNS - 1     # reserved attribute column: the per-query exclusion mask
-    MASK_PENALTY = -1.0e30                      # addend of an excluded document: it can only rank after every kept one
-
-    def _masked_search(self, s: _Schema, store: RowStore, q: np.ndarray, k: int, allowed, mult_cols, add_cols):
-        """Exact top-k of the kept documents in one scan: excluded documents get an additive score modifier of -1e30
-        through the reserved attribute column (set for this query, removed afterwards), so they sort after every kept
-        document and are dropped from the result."""
-        if len(s.attr_col) >= MAX_ATTRIBUTE_COLUMNS or len(add_cols) >= MAX_MODIFIER_TERMS:
-            raise NativeError(ERR_UNSUPPORTED, "no free attribute column / modifier term for the filter mask")
-        excluded = [num for num, doc_id in enumerate(s.doc_ids) if doc_id is not None and not allowed(num)]
-        try:
-            if excluded:
-                store.set_attributes(self.MASK_COLUMN, excluded, [1.0] * len(excluded))
-            doc, row, score = store.search_modified(q[None, :], k, mult_cols,
-                                                    list(add_cols) + [(self.MASK_COLUMN, self.MASK_PENALTY)])
-        finally:
-            if excluded:
-                store.set_attributes(self.MASK_COLUMN, excluded, None)
-        return [(int(d), int(r), float(sc)) for d, r, sc in zip(doc[0], row[0], score[0])
-                if d >= 0 and sc > self.MASK_PENALTY / 2]
 
     def _distance_from_closeness(self, closeness: float) -> float:
         if self.metric == "dotproduct":
@@ -464,7 +768,9 @@ class GpuTensorIndex:
                     continue
                 out = dict(s.fields[num] or {})
                 for f, rows in s.doc_rows[num].items():
-                    out[f] = {s.row_chunk[f][r][1]: s.stores[f].get_row(r).tolist() for r in rows}
+                    if rows:
+                        vecs = s.stores[f].get_rows(rows)
+                        out[f] = {s.row_chunk[f][r][1]: vecs[i].tolist() for i, r in enumerate(rows)}
                 if fields is not None:
                     out = {k: v for k, v in out.items() if k in fields}
                 responses.append({"status": 200, "pathId": path_id, "id": f"id:{schema}:{schema}::{doc_id}",
@@ -476,15 +782,32 @@ class GpuTensorIndex:
         responses = []
         with self._lock:
             s = self._schemas.get(schema)
+            gone: List[int] = []
             for doc_id in ids:
                 num = s.doc_num.get(doc_id) if s else None
-                if num is not None and s.doc_ids[num] is not None:
-                    self._tombstone(s, num)
-                    s.doc_ids[num] = None
-                    s.fields[num] = None
-                    del s.doc_num[doc_id]
+                if num is not None and s.doc_ids[num] is not None and num not in gone:
+                    gone.append(num)
                 responses.append({"status": 200, "pathId": f"/document/v1/{schema}/{schema}/docid/{doc_id}",
                                   "id": f"id:{schema}:{schema}::{doc_id}", "message": None})
+            if gone:    # one tombstone scatter per tensor field, one attribute clear per row store
+                for f, store in s.stores.items():
+                    rows = [r for n in gone for r in s.doc_rows[n].get(f, ())]
+                    if rows:
+                        store.delete_rows(rows)
+                        s.dead[f] = s.dead.get(f, 0) + len(rows)
+                with_attrs = [n for n in gone if s.attrs[n]]
+                if with_attrs:
+                    for store in s.stores.values():
+                        store.set_attributes(-1, with_attrs, None)
+                for num in gone:
+                    del s.doc_num[s.doc_ids[num]]
+                    s.doc_ids[num] = None
+                    s.fields[num] = None
+                    s.doc_rows[num] = {}
+                    s.attrs[num] = {}
+                s.n_live -= len(gone)
+                self._filters_update(s, gone)
+                self._maybe_compact(s)
         return _wrap("DeleteBatchResponse", {"responses": responses, "errors": False})
 
     # ------------------------------------------------------------------------------------------------ persistence
@@ -530,13 +853,16 @@ class GpuTensorIndex:
             for f, st in js["stores"].items():
                 s.stores[f] = RowStore.load(os.path.join(directory, st["file"]), device=device)
                 s.row_chunk[f] = [(int(n), str(k)) for n, k in st["row_chunk"]]
+                live = sum(len(d.get(f, ())) for d in s.doc_rows)
+                s.dead[f] = len(s.row_chunk[f]) - live
+            s.n_live = sum(1 for d in s.doc_ids if d is not None)
             ix._schemas[name] = s
         return ix
 
     def get_document_count(self, schema: str) -> int:
         with self._lock:
             s = self._schemas.get(schema)
-            return 0 if s is None else sum(1 for d in s.doc_ids if d is not None)
+            return 0 if s is None else s.n_live
 
 
 def gather_documents_from_response(response, tensor_fields_by_embeddings_field: Optional[Dict[str, str]] = None,

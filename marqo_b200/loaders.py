@@ -184,17 +184,62 @@ class B200OpenCLIP:
         import torch
         torch.cuda.synchronize(device)
 
-    def encode_text(self, sentence: Union[str, List[str]], normalize=True) -> np.ndarray:
-        """open_clip_model.py:268-286"""
-        if self.model is None:
-            self.load()
+    def _tokenize(self, sentence) -> np.ndarray:
         if self.tokenizer is None:
             raise ModelLoadError("no CLIP tokenizer available: supply model_properties['tokenizer'] "
                                  "(open_clip's BPE vocabulary is not bundled)")
         text = self.tokenizer(sentence if isinstance(sentence, list) else [sentence])
         if _is_tensor(text):
             text = text.detach().to("cpu").numpy()
-        return self.model.encode_tokens(np.asarray(text, dtype=np.int32), None, normalize=bool(normalize))
+        return np.ascontiguousarray(text, dtype=np.int32)
+
+    def encode_text(self, sentence: Union[str, List[str]], normalize=True) -> np.ndarray:
+        """open_clip_model.py:268-286"""
+        if self.model is None:
+            self.load()
+        return self.model.encode_tokens(self._tokenize(sentence), None, normalize=bool(normalize))
+
+    # -- add_documents fast path: embeddings stay in HBM (consumed by GpuTensorIndex.feed_batch as DeviceChunks) ----
+    def encode_to_device(self, inputs, default: str = 'text', normalize=True, sub_batch: int = 256, **kwargs):
+        """encode() whose result is a CUDA fp32 tensor [n, dim] on the model's device instead of a host ndarray: the
+        vectors go from the projection + L2 epilogue straight into the row store (b200_index_add_device_docs), never
+        through `List[List[float]]`.  Same routing rules as encode() (abstract_clip_model.py:56-75).  Images: uint8 HWC
+        arrays / tensors of ONE size per call; texts: strings, or an int32 [n, ctx] array of token ids."""
+        import torch
+        if self.model is None:
+            self.load()
+        infer = kwargs.pop('infer', True)
+        items = inputs if isinstance(inputs, list) else [inputs]
+        is_ids = isinstance(inputs, np.ndarray) and inputs.dtype.kind in "iu" and inputs.ndim == 2
+        is_image = not is_ids and ((infer and _is_image(inputs)) or default == 'image')
+        dev = torch.device("cuda", self.model.device)
+        n = inputs.shape[0] if is_ids else len(items)
+        out = torch.empty((n, self.model.embed_dim), dtype=torch.float32, device=dev)
+        step = max(1, min(int(sub_batch), int(self.model_properties.get("max_batch", 256))))
+        if is_image:
+            for lo in range(0, n, step):
+                part = items[lo:lo + step]
+                if all(self._on_model_device(it) for it in part):
+                    batch = torch.stack(part).contiguous()
+                else:
+                    host = np.stack([np.asarray(it.cpu() if _is_tensor(it) else
+                                                (it.convert("RGB") if type(it).__module__.startswith("PIL.") else it),
+                                                dtype=np.uint8) for it in part])
+                    batch = torch.from_numpy(host).to(dev, non_blocking=False)
+                if batch.ndim != 4 or batch.shape[3] != 3:
+                    raise UnidentifiedImageError(f"expected uint8 [n, H, W, 3] images, got {tuple(batch.shape)}")
+                self._sync_device(dev)
+                self.model.encode_images_u8_device(batch.data_ptr(), len(part), int(batch.shape[1]), int(batch.shape[2]),
+                                                   out[lo:].data_ptr(), normalize=bool(normalize), sync=True)
+        else:
+            ids = np.ascontiguousarray(inputs, dtype=np.int32) if is_ids else self._tokenize(items)
+            d_ids = torch.from_numpy(ids).to(dev)
+            self._sync_device(dev)
+            for lo in range(0, n, step):
+                m = min(step, n - lo)
+                self.model.encode_tokens_device(d_ids[lo:].data_ptr(), None, m, int(ids.shape[1]), out[lo:].data_ptr(),
+                                                normalize=bool(normalize), sync=True)
+        return out
 
 
 class B200HuggingFace:
@@ -252,6 +297,37 @@ class B200HuggingFace:
         ids = np.asarray(tok["input_ids"], dtype=np.int32)
         mask = np.asarray(tok["attention_mask"], dtype=np.int32)
         return self._model.encode_tokens(ids, mask, normalize=bool(normalize))
+
+    def encode_to_device(self, sentence, normalize=True, sub_batch: int = 64, attention_mask=None, **kwargs):
+        """encode() whose result stays on the GPU (CUDA fp32 tensor [n, dim]) for the add_documents fast path.
+        `sentence`: strings (tokenised per sub-batch with padding=True, like the reference's own sub-batching,
+        s2_inference.py:137-146), or an int32 [n, seq] array of token ids (+ optional attention_mask)."""
+        import torch
+        if self._model is None:
+            self.load()
+        dev = torch.device("cuda", self._model.device)
+        is_ids = isinstance(sentence, np.ndarray) and sentence.dtype.kind in "iu" and sentence.ndim == 2
+        items = sentence if is_ids else ([sentence] if isinstance(sentence, str) else list(sentence))
+        n = len(items)
+        out = torch.empty((n, self._model.embed_dim), dtype=torch.float32, device=dev)
+        step = max(1, min(int(sub_batch), int(self.model_properties.get("max_batch", 256))))
+        for lo in range(0, n, step):
+            if is_ids:
+                ids = np.ascontiguousarray(items[lo:lo + step], dtype=np.int32)
+                mask = None if attention_mask is None else np.ascontiguousarray(attention_mask[lo:lo + step], dtype=np.int32)
+            else:
+                if self._tokenizer is None:
+                    raise ModelLoadError("no tokenizer available: supply model_properties['tokenizer'] or 'vocab_file'")
+                tok = self._tokenizer(items[lo:lo + step], padding=True, truncation=True, max_length=self.max_seq_length,
+                                      return_tensors="np")
+                ids = np.asarray(tok["input_ids"], dtype=np.int32)
+                mask = np.asarray(tok["attention_mask"], dtype=np.int32)
+            d_ids = torch.from_numpy(ids).to(dev)
+            d_mask = None if mask is None else torch.from_numpy(mask).to(dev)
+            torch.cuda.synchronize(dev)
+            self._model.encode_tokens_device(d_ids.data_ptr(), None if d_mask is None else d_mask.data_ptr(), ids.shape[0],
+                                             ids.shape[1], out[lo:].data_ptr(), normalize=bool(normalize), sync=True)
+        return out
 
 
 LOADERS = {

@@ -114,10 +114,12 @@ def test_adapter_recognises_filtered_tensor_queries():
 
 class _NumpyRowStore:
     """CPU stand-in with RowStore's interface and arithmetic contract (fp16 rows, closeness = 1 / (2 - q.e) in fp64,
-    order (score desc, doc asc), best chunk per document) — lets the adapter's host logic run without a device."""
+    order (score desc, doc asc), best chunk per document, document bitset filter) — lets the adapter's host logic run
+    without a device."""
 
     def __init__(self, dim, metric="prenormalized-angular", device=0, capacity=0):
         self.dim, self.rows, self.docs, self.attrs = dim, [], [], {}
+        self.searches = 0
 
     def __len__(self):
         return len(self.rows)
@@ -131,6 +133,19 @@ class _NumpyRowStore:
     def delete_doc(self, doc_id):
         self.docs = [-1 if d == doc_id else d for d in self.docs]
 
+    def delete_rows(self, rows):
+        for r in rows:
+            self.docs[int(r)] = -1
+
+    def compact(self):
+        import numpy as np
+        new_of_old = np.full(len(self.rows), -1, np.int32)
+        live = [i for i, d in enumerate(self.docs) if d >= 0]
+        new_of_old[live] = np.arange(len(live))
+        self.rows = [self.rows[i] for i in live]
+        self.docs = [self.docs[i] for i in live]
+        return new_of_old
+
     def set_attributes(self, column, doc_ids, values):
         for i, d in enumerate(doc_ids):
             if column == -1:
@@ -141,12 +156,16 @@ class _NumpyRowStore:
             else:
                 self.attrs.setdefault(column, {})[int(d)] = float(values[i])
 
-    def _rank(self, q, k, mult=(), add=()):
+    def set_attributes_multi(self, columns, doc_ids, values):
+        for c, d, v in zip(columns, doc_ids, values):
+            self.attrs.setdefault(int(c), {})[int(d)] = float(v)
+
+    def _rank(self, q, k, mult=(), add=(), allowed=None):
         import numpy as np
         qh = np.asarray(q, np.float32).reshape(-1).astype(np.float16).astype(np.float64)
         best = {}
         for r, (v, d) in enumerate(zip(self.rows, self.docs)):
-            if d < 0:
+            if d < 0 or (allowed is not None and not allowed(d)):
                 continue
             c = 1.0 / (2.0 - float(v @ qh))
             if d not in best or c > best[d][0]:
@@ -158,21 +177,33 @@ class _NumpyRowStore:
             a = sum(w * self.attrs[col][d] for col, w in add if d in self.attrs.get(col, {}))
             out.append((m * c + a, d, r))
         out.sort(key=lambda t: (-t[0], t[1]))
-        doc = np.full((1, k), -1, np.int32)
-        row = np.full((1, k), -1, np.int32)
-        score = np.full((1, k), -np.inf)
+        doc = np.full(k, -1, np.int32)
+        row = np.full(k, -1, np.int32)
+        score = np.full(k, -np.inf)
         for i, (sc, d, r) in enumerate(out[:k]):
-            doc[0, i], row[0, i], score[0, i] = d, r, sc
+            doc[i], row[i], score[i] = d, r, sc
         return doc, row, score
 
-    def search(self, q, k):
-        return self._rank(q, k)
+    def search(self, q, k, mult=(), add=(), filter_bits=None, filter_docs=0, filter_tag=0):
+        import numpy as np
+        self.searches += 1
+        Q = np.atleast_2d(np.asarray(q, np.float32))
+        allowed = None
+        if filter_bits is not None:
+            bits = np.unpackbits(np.asarray(filter_bits, np.uint32).view(np.uint8), bitorder="little")
+            allowed = lambda d: d < filter_docs and bool(bits[d])
+        res = [self._rank(x, k, mult, add, allowed) for x in Q]
+        return tuple(np.stack([r[i] for r in res]) for i in range(3))
 
     def search_modified(self, q, k, mult=(), add=()):
-        return self._rank(q, k, mult, add)
+        return self.search(q, k, mult=mult, add=add)
 
     def get_row(self, r):
         return self.rows[r].astype("float32")
+
+    def get_rows(self, rows):
+        import numpy as np
+        return np.stack([self.rows[int(r)].astype("float32") for r in rows])
 
     def close(self):
         pass
@@ -266,14 +297,13 @@ def test_structured_index_filters_from_the_reference_generator():
         assert got == STRUCTURED_EXPECTED[g["filter"]], (g["filter"], g["yql"], got)
 
 
-def test_very_selective_filters_switch_to_one_masked_scan(monkeypatch):
-    """When deeper fetches hit their cap the adapter evaluates the filter over the whole schema and excludes documents
-    through the reserved attribute column — same exact answer, one scan.  The cap is lowered to force that path."""
+def test_filters_are_one_scan_through_a_document_bitset(monkeypatch):
+    """A filtered query is ONE scan whatever its selectivity: the filter is compiled to a per-document bitset once per
+    distinct filter string, kept current by feed / delete, and handed to the row store."""
     import numpy as np
     import marqo_b200.gpu_tensor_index as gti
     from _filter_scenario import _doc, _yql
     monkeypatch.setattr(gti, "RowStore", _NumpyRowStore)
-    monkeypatch.setattr(gti.GpuTensorIndex, "MAX_FETCH", 16)
     rng = np.random.default_rng(5)
     n = 200
     vecs = rng.standard_normal((n, 64)).astype(np.float32)
@@ -283,26 +313,141 @@ def test_very_selective_filters_switch_to_one_masked_scan(monkeypatch):
                            "marqo__score_modifiers": {"pop": float(i % 3 + 1)}}, {"body": (["c"], vecs[i:i + 1])})
             for i in range(n)]
     assert not ix.feed_batch(docs, "s1").errors
+    store = next(iter(ix._schemas["s1"].stores.values()))
     q = vecs[3]
     qh = q.astype(np.float16).astype(np.float64)
     c = {f"d{i}": 1.0 / (2.0 - float(vecs[i].astype(np.float16).astype(np.float64) @ qh)) for i in range(n)}
     flt = '((marqo__int_fields contains sameElement(key contains "bucket", value = 7)) OR ' \
           '(marqo__float_fields contains sameElement(key contains "bucket", value = 7)))'        # 4 of 200 documents
+    before = store.searches
     res = ix.query(_yql("s1", ["body"], 10) + f" AND {flt}", hits=10, ranking="embedding_similarity", model_restrict="s1",
                    query_features={"marqo__query_embedding": q.tolist()})
+    assert store.searches == before + 1                                   # one scan, no deeper-fetch loop
     want = sorted((d for d in c if int(d[1:]) % 50 == 7), key=lambda d: (-c[d], int(d[1:])))
     assert [h.id.split("::")[-1] for h in res.hits] == want and len(want) == 4
     assert all(abs(h.relevance - c[h.id.split("::")[-1]]) < 1e-12 for h in res.hits)
-    # together with score modifiers; and the mask column is gone afterwards (an unfiltered query sees every document)
+    entry = ix._schemas["s1"].filters[flt]
+    tag = entry.tag
+    # together with score modifiers; same filter string -> same cached bitset (tag unchanged)
     resm = ix.query(_yql("s1", ["body"], 3) + f" AND {flt}", hits=3, ranking="embedding_similarity", model_restrict="s1",
                     query_features={"marqo__query_embedding": q.tolist(), "marqo__add_weights_tensor": {"pop": 0.5}})
     wantm = sorted(want, key=lambda d: (-(c[d] + 0.5 * (int(d[1:]) % 3 + 1)), int(d[1:])))[:3]
-    assert [h.id.split("::")[-1] for h in resm.hits] == wantm
+    assert [h.id.split("::")[-1] for h in resm.hits] == wantm and entry.tag == tag
     plain = ix.query(_yql("s1", ["body"], 5), hits=5, ranking="embedding_similarity", model_restrict="s1",
                      query_features={"marqo__query_embedding": q.tolist()})
     assert [h.id.split("::")[-1] for h in plain.hits] == sorted(c, key=lambda d: (-c[d], int(d[1:])))[:5]
-    store = next(iter(ix._schemas["s1"].stores.values()))
-    assert not store.attrs.get(gti.GpuTensorIndex.MASK_COLUMN)
+    # the bitset follows the corpus: a new matching document, an overwrite that stops matching, a delete
+    extra = rng.standard_normal((1, 64)).astype(np.float32)
+    ix.feed_batch([_doc("new", {"marqo__id": "new", "marqo__int_fields": {"bucket": 7}}, {"body": (["c"], extra)}),
+                   _doc("d7", {"marqo__id": "d7", "marqo__int_fields": {"bucket": 8}}, {"body": (["c"], vecs[7:8])})], "s1")
+    ix.delete_batch(["d57"], "s1")
+    assert entry.tag != tag
+    res2 = ix.query(_yql("s1", ["body"], 10) + f" AND {flt}", hits=10, ranking="embedding_similarity", model_restrict="s1",
+                    query_features={"marqo__query_embedding": q.tolist()})
+    assert {h.id.split("::")[-1] for h in res2.hits} == {"d107", "d157", "new"}
+
+
+def test_feed_batch_is_atomic_per_document(monkeypatch):
+    """a rejected document leaves no trace — an update with a wrong dimension keeps the old version
+    searchable, a rejected new document is not registered, a multi-field document fails as a whole."""
+    import numpy as np
+    import marqo_b200.gpu_tensor_index as gti
+    from _filter_scenario import _doc, _yql
+    monkeypatch.setattr(gti, "RowStore", _NumpyRowStore)
+    rng = np.random.default_rng(6)
+    v = rng.standard_normal((4, 64)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    ix = gti.GpuTensorIndex()
+    assert not ix.feed_batch([_doc("a", {"marqo__id": "a", "t": "old"}, {"body": (["c"], v[0:1]), "title": (["c"], v[1:2])})],
+                             "s1").errors
+    bad_dim = rng.standard_normal((1, 128)).astype(np.float32)
+    r = ix.feed_batch([_doc("a", {"marqo__id": "a", "t": "new"}, {"body": (["c"], v[2:3]), "title": (["c"], bad_dim)}),
+                       _doc("b", {"marqo__id": "b"}, {"body": (["c"], bad_dim)}),
+                       _doc("c", {"marqo__id": "c"}, {"body": (["c"], np.array([[np.nan] * 64], np.float32))}),
+                       _doc("d", {"marqo__id": "d"}, {"body": (["c"], v[3:4])})], "s1")
+    assert [x.status for x in r.responses] == [400, 400, 400, 200] and r.errors
+    assert ix.get_document_count("s1") == 2
+    got = ix.get_batch(["a", "b", "c", "d"], "s1")
+    assert [x.status for x in got.responses] == [200, 404, 404, 200]
+    assert got.responses[0].document.fields["t"] == "old"
+    res = ix.query(_yql("s1", ["body"], 5), hits=5, ranking="embedding_similarity", model_restrict="s1",
+                   query_features={"marqo__query_embedding": v[0].tolist()})
+    assert [h.id.split("::")[-1] for h in res.hits][0] == "a" and abs(res.hits[0].relevance - 1.0) < 2e-3
+    # the same id twice in one batch: the last put wins, both answer 200
+    r = ix.feed_batch([_doc("e", {"marqo__id": "e", "v": 1}, {"body": (["c"], v[1:2])}),
+                       _doc("e", {"marqo__id": "e", "v": 2}, {"body": (["c"], v[2:3])})], "s1")
+    assert [x.status for x in r.responses] == [200, 200]
+    assert ix.get_batch(["e"], "s1").responses[0].document.fields["v"] == 2
+    s = ix._schemas["s1"]
+    assert len(s.doc_rows[s.doc_num["e"]]["marqo__embeddings_body"]) == 1
+
+
+def test_update_heavy_feed_compacts_the_matrix(monkeypatch):
+    """Replaced versions are tombstoned by row, and the dead rows are squeezed out once they are a sizeable share."""
+    import numpy as np
+    import marqo_b200.gpu_tensor_index as gti
+    from _filter_scenario import _doc, _yql
+    monkeypatch.setattr(gti, "RowStore", _NumpyRowStore)
+    monkeypatch.setattr(gti.GpuTensorIndex, "COMPACT_MIN_DEAD", 8)
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal((40, 64)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    ix = gti.GpuTensorIndex()
+    ix.feed_batch([_doc(f"d{i}", {"marqo__id": f"d{i}"}, {"body": (["a", "b"], v[2 * i:2 * i + 2])}) for i in range(10)], "s1")
+    s = ix._schemas["s1"]
+    store = s.stores["marqo__embeddings_body"]
+    for rnd in range(3):
+        ix.feed_batch([_doc(f"d{i}", {"marqo__id": f"d{i}", "round": rnd}, {"body": (["a", "b"], v[2 * i + 20:2 * i + 22])})
+                       for i in range(10)], "s1")
+    assert s.epoch >= 1 and len(store) < 20 + 3 * 20               # compaction ran
+    assert len(store) - s.dead["marqo__embeddings_body"] == 20
+    res = ix.query(_yql("s1", ["body"], 3), hits=3, ranking="embedding_similarity", model_restrict="s1",
+                   query_features={"marqo__query_embedding": v[27].tolist()})
+    top = res.hits[0]
+    assert top.id.endswith("::d3") and abs(top.relevance - 1.0) < 2e-3
+    assert top.dict()["fields"]["matchfeatures"]["closest(marqo__embeddings_body)"]["cells"] == {"1": 1.0}
+    got = ix.get_batch(["d3"], "s1").responses[0].document.fields
+    assert got["round"] == 2 and list(got["marqo__embeddings_body"]) == ["0", "1"]
+
+
+def test_concurrent_queries_share_scans(monkeypatch):
+    """Marqo sends one query per request from up to 8 threads (api/configs.py:27-28): requests that are in flight
+    together and agree on (row store, modifiers, filter) are gathered into one scan; every caller gets its own hits."""
+    import threading
+    import time
+    import numpy as np
+    import marqo_b200.gpu_tensor_index as gti
+    from _filter_scenario import _doc, _yql
+
+    class _Slow(_NumpyRowStore):
+        def search(self, q, k, **kw):
+            time.sleep(0.02)                                       # a scan in flight: later arrivals pile up behind it
+            return super().search(q, k, **kw)
+
+    monkeypatch.setattr(gti, "RowStore", _Slow)
+    rng = np.random.default_rng(8)
+    n = 64
+    v = rng.standard_normal((n, 64)).astype(np.float32)
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    ix = gti.GpuTensorIndex(coalesce_window_s=0.01)
+    ix.feed_batch([_doc(f"d{i}", {"marqo__id": f"d{i}"}, {"body": (["c"], v[i:i + 1])}) for i in range(n)], "s1")
+    out = {}
+
+    def ask(i):
+        res = ix.query(_yql("s1", ["body"], 3 + i % 3), hits=3 + i % 3, ranking="embedding_similarity", model_restrict="s1",
+                       query_features={"marqo__query_embedding": v[i].tolist()})
+        out[i] = [h.id.split("::")[-1] for h in res.hits]
+
+    threads = [threading.Thread(target=ask, args=(i,)) for i in range(24)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    for i in range(24):
+        assert out[i][0] == f"d{i}" and len(out[i]) == 3 + i % 3
+    st = ix.coalescer_stats()
+    assert st["queries"] == 24 and st["batches"] < 24              # at least some requests shared a scan
+    # a lone caller is not delayed by the gathering window and still gets the right answer
+    ask(5)
+    assert out[5][0] == "d5"
 
 
 def test_index_scenarios_on_the_cpu_stand_in(monkeypatch):
@@ -313,11 +458,11 @@ def test_index_scenarios_on_the_cpu_stand_in(monkeypatch):
     from _filter_scenario import run_feed_query_scenario, run_score_modifier_scenario
 
     class _Store(_NumpyRowStore):
-        def search_modified(self, q, k, mult=(), add=()):
-            # the engine refuses negative multipliers on indexes with explicit document ids (b200_index_search_modified)
+        def search(self, q, k, mult=(), add=(), **kw):
+            # the engine refuses negative multipliers on indexes with explicit document ids (b200_index_search_ex)
             if any(w * v < 0 for col, w in mult for v in self.attrs.get(col, {}).values()):
                 raise N.NativeError(N.ERR_UNSUPPORTED, "negative multiplier")
-            return super().search_modified(q, k, mult, add)
+            return super().search(q, k, mult=mult, add=add, **kw)
 
     monkeypatch.setattr(gti, "RowStore", _Store)
     run_feed_query_scenario()
