@@ -1,3 +1,6 @@
+#include <cstdlib>
+#include <cstring>
+
 #include "attention.cuh"
 
 namespace mb {
@@ -228,10 +231,14 @@ attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restric
 int launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
            cudaStream_t stream) {
     if (B <= 0 || S <= 0) return 0;
-    // Sequences of at least one full 128-row tile run on the tcgen05 kernel (attention_tc.cu).  Shorter ones
-    // (ViT-B-32: 50 tokens, CLIP text: 77) would leave most of a 128 x 128 tile masked; the 64-row warp-level
-    // kernel below wastes far less on them (measured on B200: 0.33 ms vs 0.72 ms per ViT-B-32 step).
-    if (S >= 128) {
+    // Every sequence length runs on the tcgen05 kernel (attention_tc.cu); sequences shorter than one 128-row tile are
+    // packed several to a tile under a block-diagonal mask.  MARQO_B200_ATTN_SHORT=mma selects the warp-level
+    // mma.sync kernel below for S < 128 (kept for A/B timing only).
+    static const bool short_on_mma = [] {
+        const char* e = getenv("MARQO_B200_ATTN_SHORT");
+        return e != nullptr && strcmp(e, "mma") == 0;
+    }();
+    if (S >= 128 || !short_on_mma) {
         return launch_tc(qkv, out, B, S, W, H, mask, kv_len, stream);
     }
     if (W != H * HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);

@@ -69,6 +69,53 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// tcgen05.wait::ld that names the registers an in-flight tcgen05.ld fills: every use of v[] after this statement depends
+// on it, so the compiler cannot schedule arithmetic on a prefetched chunk ahead of the wait.
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+// One 32-key chunk of a score row: p = exp2(s * scale - m_safe) for the keys in [klo, khi) (block-local indices), 0 for
+// the others; running raw maximum, row sum, bf16 P into the K-major 128B-swizzled A-operand layout.
+template <bool FULL>
+__device__ __forceinline__ void softmax_chunk(const uint32_t (&v)[32], int c, int klo, int khi, float scale_log2e,
+                                              float m_safe, float& lsum, float& mx, uint8_t* sP, int r) {
+    uint32_t pk[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+        float p0, p1;
+        if (FULL) {
+            mx = fmaxf(mx, fmaxf(s0, s1));
+            p0 = ex2(fmaf(s0, scale_log2e, -m_safe));
+            p1 = ex2(fmaf(s1, scale_log2e, -m_safe));
+        } else {
+            const int k0 = c * 32 + i;
+            const bool ok0 = k0 >= klo && k0 < khi, ok1 = k0 + 1 >= klo && k0 + 1 < khi;
+            mx = ok0 ? fmaxf(mx, s0) : mx;
+            mx = ok1 ? fmaxf(mx, s1) : mx;
+            p0 = ok0 ? ex2(fmaf(s0, scale_log2e, -m_safe)) : 0.f;
+            p1 = ok1 ? ex2(fmaf(s1, scale_log2e, -m_safe)) : 0.f;
+        }
+        lsum += p0 + p1;
+        pk[i >> 1] = pack2(p0, p1);
+    }
+    // keys c*32 .. c*32+31 -> chunk (c >> 1), 16-byte units (c & 1) * 4 .. +3 of row r
+    uint8_t* rowp = sP + (size_t)(c >> 1) * (BQ * 128) + (size_t)r * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int unit = (c & 1) * 4 + u;
+        *reinterpret_cast<uint4*>(rowp + ((unit ^ (r & 7)) << 4)) =
+            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+    }
+}
+
 // work item -> (batch, head, query block); consecutive items share (batch, head) so the two CTAs that process them
 // at the same time read K / V once from HBM and once from L2
 struct Item {
@@ -84,9 +131,18 @@ __device__ __forceinline__ Item decode_item(int it, int q_blocks, int H) {
     return w;
 }
 
-template <int MASK>
+// PACKED (S < 128): an item is a GROUP of pack = 128 / S consecutive sequences sharing one 128-row tile; w.b is the
+// group index, the tile's valid rows / keys are the group's nseq * S tokens and the mask is block-diagonal (a row only
+// sees the keys of its own sequence) — see the softmax warps.
+template <int MASK, bool PACKED>
 __device__ __forceinline__ void item_extent(const Item& w, int S, int s_main, const int32_t* kv_len, int& len, int& kend,
-                                            int& nkb) {
+                                            int& nkb, int pack = 1, int B = 0) {
+    if (PACKED) {
+        const int nseq = max(0, min(pack, B - w.b * pack));
+        len = kend = nseq * S;
+        nkb = nseq > 0 ? 1 : 0;
+        return;
+    }
     len = S;
     if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[w.b], 0));
     kend = min(len, s_main);
@@ -94,11 +150,14 @@ __device__ __forceinline__ void item_extent(const Item& w, int S, int s_main, co
     nkb = (kend + BKV - 1) / BKV;
 }
 
-template <int MASK>
-__global__ void __launch_bounds__(THREADS, 2)
+// 224 threads x 144 registers x 2 CTAs = 64512 of the SM's 65536 registers: __launch_bounds__(224, 2) would make ptxas
+// budget for 256-thread CTAs (128 registers) and spill the prefetched score chunk.
+template <int MASK, bool PACKED>
+__global__ void __maxnreg__(144)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ qkv,
                     __nv_bfloat16* __restrict__ out, int S, int W, int H, const int32_t* __restrict__ kv_len,
-                    float scale_log2e, int s_main, int inline_tail_rows, int q_blocks, int total_items) {
+                    float scale_log2e, int s_main, int inline_tail_rows, int q_blocks, int total_items, int pack, int B) {
+    const int stride = PACKED ? pack * S : S;   // rows between the bases of consecutive sequences / groups
     // Keys [0, s_main) go through the tensor cores in blocks of 128; the few keys [s_main, S) of a sequence length
     // such as 257 = 2 * 128 + 1 (ViT class token) are folded in on the CUDA cores in the epilogue instead of paying
     // for a whole extra 128-wide block.
@@ -159,8 +218,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
             for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n) {
                 const Item w = decode_item(it, q_blocks, H);
                 int len, kend, nkb;
-                item_extent<MASK>(w, S, s_main, kv_len, len, kend, nkb);
-                const int row_base = w.b * S;
+                item_extent<MASK, PACKED>(w, S, s_main, kv_len, len, kend, nkb, pack, B);
+                const int row_base = w.b * stride;
                 if (n > 0) ptx::mbar_wait(q_empty, (n - 1) & 1);   // the previous item's last S MMA has read Q
                 ptx::mbar_arrive_expect_tx(q_full, Q_BYTES);
                 ptx::tma_load_2d(sQ, &tmap, q_full, w.h * HD, row_base + w.q0, ptx::kEvictNormal);
@@ -191,7 +250,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
             while (c.it < total_items) {
                 const Item w = decode_item(c.it, q_blocks, H);
                 int len, kend;
-                item_extent<MASK>(w, S, s_main, kv_len, len, kend, c.nkb);
+                item_extent<MASK, PACKED>(w, S, s_main, kv_len, len, kend, c.nkb, pack, B);
                 if (c.nkb > 0) return;
                 if (owns_q) {
                     ptx::mbar_wait(q_full, c.n & 1);
@@ -280,8 +339,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n) {
             const Item w = decode_item(it, q_blocks, H);
             int len, kend, nkb;
-            item_extent<MASK>(w, S, s_main, kv_len, len, kend, nkb);
-            const int row_base = w.b * S;
+            item_extent<MASK, PACKED>(w, S, s_main, kv_len, len, kend, nkb, pack, B);
+            const int row_base = w.b * stride;
             const bool do_row = inline_tail_rows > 0 && w.qb == q_blocks - 1;
             const int trow = s_main;   // the remainder row / key index
             ptx::mbar_wait(q_full, n & 1);
@@ -295,7 +354,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                     const int nxt = it + gridDim.x;
                     if (lane == 0 && nxt < total_items) {   // the next item's remainder rows: into L2 ahead of time
                         const Item wn = decode_item(nxt, q_blocks, H);
-                        const __nv_bfloat16* nrow = qkv + ((size_t)wn.b * S + s_main) * ld + W + wn.h * HD;
+                        const __nv_bfloat16* nrow = qkv + ((size_t)wn.b * stride + s_main) * ld + W + wn.h * HD;
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + W));
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow - W));
@@ -474,10 +533,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
             const Item w = decode_item(it, q_blocks, H);
             int len, kend, nkb;
-            item_extent<MASK>(w, S, s_main, kv_len, len, kend, nkb);
-            const int row_base = w.b * S;  // first row of this sequence in the packed [B*S, 3W] matrix
-            const int qrow = w.q0 + r;     // position in the sequence
+            item_extent<MASK, PACKED>(w, S, s_main, kv_len, len, kend, nkb, pack, B);
+            const int row_base = w.b * stride;  // first row of this sequence / group in the packed [B*S, 3W] matrix
+            const int qrow = w.q0 + r;     // position in the sequence (PACKED: row of the tile)
             const int h = w.h;
+            // PACKED: this row's sequence inside the group and the keys it may see (block-diagonal mask)
+            int p_lo = 0, p_hi = 0;
+            bool row_valid = qrow < S;
+            if (PACKED) {
+                const int sidx = r / S;
+                row_valid = sidx < pack && w.b * pack + sidx < B;
+                if (row_valid) {
+                    p_lo = sidx * S;
+                    int n = S;
+                    if (MASK == MASK_KEYLEN) n = min(S, max(kv_len[w.b * pack + sidx], 0));
+                    p_hi = p_lo + n;
+                    if (MASK == MASK_CAUSAL) p_hi = min(p_hi, r + 1);
+                }
+            }
             float m_run = -INFINITY, l_run = 0.f;
             // The remainder key (257 = 2 * 128 + 1) is folded in on the CUDA cores in the epilogue from the scores and
             // the V row that warp 6 stages in shared memory.
@@ -487,67 +560,80 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                 const uint32_t par = g & 1;
                 ptx::mbar_wait(s_full, par);
                 ptx::tc_fence_after();
-                int limit = kend - j * BKV;  // keys with block-local index >= limit are masked
-                if (MASK == MASK_CAUSAL) limit = min(limit, qrow - j * BKV + 1);
-                const bool full = limit >= BKV;
-                // pass 1: row maximum of this block
-                float mx = -INFINITY;
-#pragma unroll 1
-                for (int c = 0; c < BKV / 32; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, v);
-                    ptx::tmem_ld_wait();
-                    if (full) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (c * 32 + i < limit) mx = fmaxf(mx, __uint_as_float(v[i]));
-                    }
+                int khi = kend - j * BKV;  // keys with block-local index outside [klo, khi) are masked
+                if (MASK == MASK_CAUSAL) khi = min(khi, qrow - j * BKV + 1);
+                int klo = 0;
+                if (PACKED) {
+                    klo = p_lo;
+                    khi = p_hi;
                 }
-                mx *= scale_log2e;  // scale > 0: max commutes with the scaling
-                const float m_new = fmaxf(m_run, mx);
-                const float m_safe = m_new == -INFINITY ? 0.f : m_new;
-                const float alpha = ex2(m_run - m_safe);  // 0 on the first block
+                const bool full = klo <= 0 && khi >= BKV;
+                // ONE pass over the scores (the two-pass version read S twice from TMEM and waited for each of its eight
+                // loads).  The exponent reference m_ref is NOT the exact block maximum: it is the running reference of
+                // the row (first block: the maximum of the row's first 32 scores), so later blocks need no rescale of
+                // O at all.  The exact maximum is tracked on the side; only if it exceeds the reference by more than
+                // 2^8 (P would outgrow bf16's useful range / risk overflow) the warp falls back to the exact two-pass
+                // update below.  exp2(s - m_ref) <= 256, sums stay far inside fp32.
+                uint32_t va[32], vb[32];
+                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL, va);
+                tmem_ld_wait_regs(va);
+                float m_ref = m_run;
+                if (j == 0) {
+                    float c0 = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (full || (i >= klo && i < khi)) c0 = fmaxf(c0, __uint_as_float(va[i]));
+                    m_ref = c0 * scale_log2e;   // scale > 0: max commutes with the scaling
+                }
+                const float m_safe = m_ref == -INFINITY ? 0.f : m_ref;
                 // P buffer and O accumulator are free again (the previous item's last PV was awaited in its epilogue)
                 if (j > 0) ptx::mbar_wait(pv_done, par ^ 1);
-                // pass 2: p = exp2(s - m), row sum, bf16 P into the K-major 128B-swizzled A-operand layout
-                float lsum = 0.f;
+                float lsum = 0.f, mx = -INFINITY;
+                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 32, vb);      // chunk c + 1 is in flight while chunk c is
+                if (full) softmax_chunk<true>(va, 0, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);   // processed
+                else softmax_chunk<false>(va, 0, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                tmem_ld_wait_regs(vb);
+                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 64, va);
+                if (full) softmax_chunk<true>(vb, 1, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                else softmax_chunk<false>(vb, 1, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                tmem_ld_wait_regs(va);
+                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 96, vb);
+                if (full) softmax_chunk<true>(va, 2, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                else softmax_chunk<false>(va, 2, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                tmem_ld_wait_regs(vb);
+                if (full) softmax_chunk<true>(vb, 3, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                else softmax_chunk<false>(vb, 3, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                float alpha = 1.f;
+                float m_new = m_ref;
+                const float m_true = fmaxf(m_ref, mx * scale_log2e);
+                const bool exceeded = m_true > m_safe + 8.0f;
+                if (__any_sync(0xffffffffu, exceeded)) {   // warp-uniform: tcgen05.ld / st are warp-collective
+                    // exact update for this block: reference = true running maximum, P recomputed, O rescaled
+                    m_new = m_true;
+                    const float ms2 = m_new == -INFINITY ? 0.f : m_new;
+                    alpha = ex2(m_run - ms2);   // 0 on the first block; 1 for rows whose maximum did not move
+                    lsum = 0.f;
+                    float dummy = -INFINITY;
 #pragma unroll 1
-                for (int c = 0; c < BKV / 32; ++c) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, v);
-                    ptx::tmem_ld_wait();
-                    uint32_t pk[16];
-                    if (full) {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float p0 = ex2(fmaf(__uint_as_float(v[i]), scale_log2e, -m_safe));
-                            const float p1 = ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2e, -m_safe));
-                            lsum += p0 + p1;
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(p0, p1);
-                            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const float p0 =
-                                c * 32 + i < limit ? ex2(fmaf(__uint_as_float(v[i]), scale_log2e, -m_safe)) : 0.f;
-                            const float p1 =
-                                c * 32 + i + 1 < limit ? ex2(fmaf(__uint_as_float(v[i + 1]), scale_log2e, -m_safe)) : 0.f;
-                            lsum += p0 + p1;
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(p0, p1);
-                            pk[i >> 1] = *reinterpret_cast<uint32_t*>(&t2);
-                        }
+                    for (int c = 0; c < BKV / 32; ++c) {
+                        ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, va);
+                        tmem_ld_wait_regs(va);
+                        if (full) softmax_chunk<true>(va, c, klo, khi, scale_log2e, ms2, lsum, dummy, sP, r);
+                        else softmax_chunk<false>(va, c, klo, khi, scale_log2e, ms2, lsum, dummy, sP, r);
                     }
-                    // keys c*32 .. c*32+31 -> chunk (c >> 1), 16-byte units (c & 1) * 4 .. +3 of row r
-                    uint8_t* rowp = sP + (size_t)(c >> 1) * (BQ * 128) + (size_t)r * 128;
+                    if (j > 0) {
+                        // rescale the running output by alpha (thread-local: lane == row)
+#pragma unroll 1
+                        for (int c = 0; c < HD / 32; ++c) {
+                            ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + c * 32, va);
+                            tmem_ld_wait_regs(va);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int unit = (c & 1) * 4 + u;
-                        *reinterpret_cast<uint4*>(rowp + ((unit ^ (r & 7)) << 4)) =
-                            make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+                            for (int i = 0; i < 32; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) * alpha);
+                            ptx::tmem_st_32x32b_x32(lane_addr + O_COL + c * 32, va);
+                        }
+                        ptx::tmem_st_wait();
+                    } else {
+                        alpha = 0.f;   // nothing accumulated yet (l_run == 0)
                     }
                 }
                 l_run = l_run * alpha + lsum;
@@ -556,19 +642,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(s_free);
-                if (j > 0) {
-                    // rescale the running output by alpha (thread-local: lane == row)
-#pragma unroll 1
-                    for (int c = 0; c < HD / 32; ++c) {
-                        uint32_t v[32];
-                        ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + c * 32, v);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-                        ptx::tmem_st_32x32b_x32(lane_addr + O_COL + c * 32, v);
-                    }
-                    ptx::tmem_st_wait();
-                }
                 ptx::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -608,7 +681,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
 #pragma unroll
                     for (int i = 0; i < HD / 2; ++i) o[i] = 0.f;
                 }
-                if (qrow < S) {
+                if (row_valid) {
                     if (has_tail_key) {   // o = o * alpha + p * v (alpha = 1, p = 0 for rows the key is masked for)
                         const uint4* vp = reinterpret_cast<const uint4*>(sTailV) + hf * 4;   // broadcast reads
 #pragma unroll
@@ -663,47 +736,76 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     if (W != H * tc::HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);
     static std::once_flag once;
     std::call_once(once, [] {
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tc::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_CAUSAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tc::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_KEYLEN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)tc::SMEM_BYTES));
+        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_NONE, false>, attr, (int)tc::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_CAUSAL, false>, attr, (int)tc::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_KEYLEN, false>, attr, (int)tc::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_NONE, true>, attr, (int)tc::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_CAUSAL, true>, attr, (int)tc::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_KEYLEN, true>, attr, (int)tc::SMEM_BYTES));
     });
     // one tensor map over the packed [B*S, 3W] matrix serves Q, K and V tiles (64 columns x 128 rows, 128B swizzle);
     // rows past the end of the matrix are zero-filled, rows of the next sequence are masked by key index
     CUtensorMap tmap = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,
                                     (uint64_t)3 * W * 2, tc::HD, tc::BQ, CU_TENSOR_MAP_SWIZZLE_128B);
+    const float scale_log2e = 0.125f * 1.4426950408889634f;
+    int device = 0;
+    MB_CUDA(cudaGetDevice(&device));
+    if (S < tc::BQ) {
+        // Short sequences (ViT-B-32: 50 tokens, CLIP text: 77, short BERT batches): pack = 128 / S whole sequences share
+        // one 128 x 128 tile under a block-diagonal mask — S = 50 fills 100 of the 128 rows instead of 50.
+        const int pack = tc::BQ / S;
+        const int groups = (B + pack - 1) / pack;
+        const int total_items = groups * H;
+        const int grid = std::min(2 * sm_count(device), total_items);
+        auto run = [&](auto kern) {
+            kern<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, H, kv_len, scale_log2e,
+                                                              /*s_main=*/1 << 30, 0, /*q_blocks=*/1, total_items, pack, B);
+        };
+        switch (mask) {
+            case MASK_NONE:
+                run(tc::attention_tc_kernel<MASK_NONE, true>);
+                break;
+            case MASK_CAUSAL:
+                run(tc::attention_tc_kernel<MASK_CAUSAL, true>);
+                break;
+            case MASK_KEYLEN:
+                if (!kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
+                run(tc::attention_tc_kernel<MASK_KEYLEN, true>);
+                break;
+            default:
+                fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);
+        }
+        MB_CUDA(cudaGetLastError());
+        return 1;
+    }
     // A remainder of ONE token (S = 257, 129, ...: a class token on top of a power-of-two grid) is not worth a 128-wide
     // tile in either dimension: warp 6 of the kernel handles that key and that query row.
     const int rem = S % tc::BQ;
     const bool tail = S > tc::BQ && rem == 1;
     const int s_main = tail ? S - rem : S;                       // keys handled by the tensor cores
     const int q_blocks = tail ? S / tc::BQ : (S + tc::BQ - 1) / tc::BQ;
-    const float scale_log2e = 0.125f * 1.4426950408889634f;
     const int inline_rows = tail ? rem : 0;
     // persistent grid: two CTAs per SM; an odd CTA count when q_blocks is even makes every CTA alternate between the
     // query blocks of a sequence, so the remainder-row work of the last block is spread over all CTAs
     const int total_items = B * H * q_blocks;
-    int device = 0;
-    MB_CUDA(cudaGetDevice(&device));
     int grid = 2 * sm_count(device);
     if ((q_blocks & 1) == 0 && (grid & 1) == 0) grid -= 1;
     grid = std::min(grid, total_items);
     auto run = [&](auto kern) {
         kern<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, H, kv_len, scale_log2e, s_main, inline_rows,
-                                                          q_blocks, total_items);
+                                                          q_blocks, total_items, 1, B);
     };
     switch (mask) {
         case MASK_NONE:
-            run(tc::attention_tc_kernel<MASK_NONE>);
+            run(tc::attention_tc_kernel<MASK_NONE, false>);
             break;
         case MASK_CAUSAL:
-            run(tc::attention_tc_kernel<MASK_CAUSAL>);
+            run(tc::attention_tc_kernel<MASK_CAUSAL, false>);
             break;
         case MASK_KEYLEN:
             if (!kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
-            run(tc::attention_tc_kernel<MASK_KEYLEN>);
+            run(tc::attention_tc_kernel<MASK_KEYLEN, false>);
             break;
         default:
             fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);

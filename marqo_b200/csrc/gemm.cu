@@ -1,5 +1,6 @@
 #include "gemm.cuh"
 
+#include <cstdlib>
 #include <mutex>
 
 #include "ptx.cuh"
@@ -10,18 +11,29 @@ namespace gemm {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 8;  // two warps per TMEM sub-partition, each draining one half of the tile's columns
-constexpr int THREADS = 64 + 32 * EPI_WARPS;  // warp 0 TMA, warp 1 MMA, warps 2.. epilogue
+// Epilogue warps (warp 0 TMA, warp 1 MMA, warps 2.. epilogue):
+//   EW = 8   general epilogue (fp32 / residual / token scatter): two warps per TMEM sub-partition, each draining one
+//            half of the tile's columns through a 32 x 128 B transpose buffer.
+//   EW = 16  bf16-out GEMMs without residual (QKV, fc1 + GELU): FOUR warps per sub-partition, a quarter of the columns
+//            each.  The r01 profile of fc1 showed the 8-warp epilogue at 49 % issue-active with two warps per scheduler
+//            (31 % of their stall samples fixed-latency dependencies, 16 % tcgen05.ld waits) while the tensor pipe idled
+//            at 62 %: the erf-GELU epilogue took as long as the tile's MMAs.  Twice the warps = twice the independent
+//            instruction streams per scheduler to hide those latencies; the staging buffer shrinks to 32 x 64 B per
+//            warp so the smem ring keeps its depth.
 constexpr int ACC_STAGES = 2;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;
 constexpr int SMEM_LIMIT = 232448;
 
-template <int BN>
+template <int BN, int EW>
 struct Cfg {
+    static constexpr int THREADS = 64 + 32 * EW;
     static constexpr uint32_t B_STAGE_BYTES = (BN / 2) * BK * 2;   // each CTA of the pair holds half of the W tile
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-    // per epilogue warp: a 32-row x 128-byte transpose buffer (coalesced global I/O) + a 128-byte bias row
-    static constexpr uint32_t EPI_BYTES = 8 /*EPI_WARPS*/ * (32 * 128 + 128);
+    // per epilogue warp: a 32-row transpose buffer (128-byte rows; 64-byte rows for EW = 16) + a 128-byte bias row
+    static constexpr uint32_t EPI_ROW_BYTES = EW == 16 ? 64 : 128;
+    // (EW = 16 keeps the bias row inside the transpose buffer, so the smem ring stays 6 stages deep at BN = 256)
+    static constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_ROW_BYTES + (EW == 16 ? 0 : 128);
+    static constexpr uint32_t EPI_BYTES = EW * EPI_WARP_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - (int)EPI_BYTES) / (int)STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;
@@ -78,10 +90,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int BN, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, EW>;
+    constexpr int EPI_WARPS = EW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -182,6 +195,84 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
+    } else if (warp >= 2 && EW == 16) {
+        // ---------------------------------------------------------------- fast bf16 epilogue (16 warps)
+        // lane == accumulator row; each warp drains 32 rows x (BN / 4) columns in 32-column chunks:
+        // bias -> activation -> bf16 -> 32 x 64 B swizzled staging buffer -> 64-byte coalesced row segments.
+        const int sp = warp & 3;
+        const int part = (warp - 2) >> 2;                  // column quarter of the tile
+        constexpr int PART_COLS = BN / 4;
+        constexpr int CHUNKS = PART_COLS / 32;
+        static_assert(EW != 16 || (BN % 128 == 0), "the 16-warp epilogue needs whole 32-column chunks per quarter");
+        const Epilogue& ep = p.ep;
+        uint8_t* stage_buf = smem_epi + (size_t)(warp - 2) * C::EPI_WARP_BYTES;
+        float* bias_row = reinterpret_cast<float*>(stage_buf);   // first 128 B of the buffer, consumed before it is filled
+        const int frow = lane >> 2, funit = lane & 3;      // flush phase: 8 rows x 4 sixteen-byte units per instruction
+        const int wswz = (lane >> 1) & 3;                  // write-phase swizzle of this lane's own row
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = cluster_id; t < num_super; t += num_clusters) {
+            const int m0 = ((t / p.tiles_n) * CLUSTER + (int)crank) * BM;
+            const int nt0 = (t % p.tiles_n) * BN + part * PART_COLS;
+            const int wrow0 = m0 + sp * 32;
+            ptx::mbar_wait(&tfull[acc], acc_phase);
+            ptx::tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < CHUNKS; ++c) {
+                const int n0 = nt0 + c * 32;
+                const bool cols_ok = n0 < p.N;
+                float bias_v = 0.f;
+                if (ep.bias && cols_ok) bias_v = __ldg(ep.bias + n0 + lane);
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(sp * 32) << 16) + acc * BN + part * PART_COLS + c * 32, v);
+                ptx::tmem_ld_wait();
+                if (c == CHUNKS - 1) {
+                    // this warp's share of the accumulator is in registers: hand it back to the MMA warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty[acc]), 0));
+                }
+                if (cols_ok) {
+                    bias_row[lane] = bias_v;
+                    __syncwarp();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 b = *reinterpret_cast<const float4*>(bias_row + 4 * j);   // broadcast read
+                        f[4 * j] = __uint_as_float(v[4 * j]) + b.x;
+                        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                    }
+                    __syncwarp();   // every lane has read the bias row: the buffer may be overwritten
+                    if (ep.act != ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(stage_buf + lane * 64 + ((j ^ wswz) << 4)) =
+                            make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                       pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                    __syncwarp();
+                    const int col = n0 + funit * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + frow;
+                        const int grow = wrow0 + rr;
+                        if (grow < p.M) {
+                            const uint4 val = *reinterpret_cast<const uint4*>(stage_buf + rr * 64 + ((funit ^ ((rr >> 1) & 3)) << 4));
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ep.out) + ((size_t)grow * ep.ldo + col) * 2) = val;
+                        }
+                    }
+                    __syncwarp();   // the buffer (and bias_row) are reused by the next chunk
+                }
+            }
+            if (++acc == ACC_STAGES) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
     } else if (warp >= 2) {
         // ---------------------------------------------------------------- epilogue (TMEM -> regs -> smem -> global)
         // A warp may only read the TMEM lanes of sub-partition (warp % 4); the two warps that share a sub-partition
@@ -194,7 +285,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         constexpr int CHUNKS = HALF_COLS / 32;
         const bool has_cols = half * HALF_COLS < BN;  // BN = 32 would leave the second half empty
         const Epilogue& ep = p.ep;
-        uint8_t* stage_buf = smem_epi + (size_t)(warp - 2) * (32 * 128 + 128);
+        uint8_t* stage_buf = smem_epi + (size_t)(warp - 2) * C::EPI_WARP_BYTES;
         float* bias_row = reinterpret_cast<float*>(stage_buf + 32 * 128);
         const int esz = ep.out_fp32 ? 4 : 2;                  // output element size
         const int cols_per_flush = 128 / esz;                 // 32 fp32 or 64 bf16 columns fill a 128-byte row
@@ -362,16 +453,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
 void configure() {
     static std::once_flag once;
     std::call_once(once, [] {
-        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)Cfg<256>::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)Cfg<128>::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)Cfg<64>::SMEM_BYTES));
+        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 8>, attr, (int)Cfg<256, 8>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 8>, attr, (int)Cfg<128, 8>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<64, 8>, attr, (int)Cfg<64, 8>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 16>, attr, (int)Cfg<256, 16>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 16>, attr, (int)Cfg<128, 16>::SMEM_BYTES));
     });
 }
 
-template <int BN>
+template <int BN, int EW>
 static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const Epilogue& ep,
                       int sms, cudaStream_t stream) {
     Params p;
@@ -391,8 +482,8 @@ static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     const int clusters = std::min(p.super_m * p.tiles_n, max_clusters);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * CLUSTER);
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = Cfg<BN>::SMEM_BYTES;
+    cfg.blockDim = dim3(Cfg<BN, EW>::THREADS);
+    cfg.dynamicSmemBytes = Cfg<BN, EW>::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -401,7 +492,7 @@ static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MB_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN>, ta, tb, p));
+    MB_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EW>, ta, tb, p));
 }
 
 void launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const Epilogue& ep, int sms,
@@ -411,13 +502,23 @@ void launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int 
     if (N % 32 != 0) fail(B200_ERR_INTERNAL, "gemm: N = %d must be a multiple of 32", N);
     if (lda % 8 != 0 || ep.ldo % 8 != 0) fail(B200_ERR_INTERNAL, "gemm: leading dimensions must be multiples of 8");
     configure();
+    // bf16 output, no residual / token scatter (QKV, fc1): the 16-warp epilogue.  MARQO_B200_GEMM_EPI8=1 keeps the
+    // general 8-warp epilogue for A/B timing.
+    static const bool force8 = [] {
+        const char* e = getenv("MARQO_B200_GEMM_EPI8");
+        return e != nullptr && e[0] == '1';
+    }();
+    const bool fast = !force8 && !ep.out_fp32 && ep.residual == nullptr && ep.rowbias == nullptr && ep.remap_group == 0;
     // Largest tile that wastes no columns, otherwise the widest one.
-    if (N % 256 == 0 || N > 512)
-        launch_bn<256>(A, lda, W, M, N, K, ep, sms, stream);
-    else if (N % 128 == 0 || N > 128)
-        launch_bn<128>(A, lda, W, M, N, K, ep, sms, stream);
-    else
-        launch_bn<64>(A, lda, W, M, N, K, ep, sms, stream);
+    if (N % 256 == 0 || N > 512) {
+        if (fast) launch_bn<256, 16>(A, lda, W, M, N, K, ep, sms, stream);
+        else launch_bn<256, 8>(A, lda, W, M, N, K, ep, sms, stream);
+    } else if (N % 128 == 0 || N > 128) {
+        if (fast) launch_bn<128, 16>(A, lda, W, M, N, K, ep, sms, stream);
+        else launch_bn<128, 8>(A, lda, W, M, N, K, ep, sms, stream);
+    } else {
+        launch_bn<64, 8>(A, lda, W, M, N, K, ep, sms, stream);
+    }
 }
 
 }  // namespace gemm

@@ -20,9 +20,14 @@ q = rng.standard_normal((64, d)).astype(np.float32)
 q /= np.linalg.norm(q, axis=1, keepdims=True)
 q[0] = corpus[17]
 lo, hi = shard_bounds(n, rank, world)
-store = ShardedRowStore(RowStore(d, device=local), rank, world, device=dev)
+corpus[100:130] = corpus[17]                    # > 16 exact ties inside shard 0: the guard + collect pass under exchange
+mode = os.environ.get("B200_EXCHANGE", "auto")
+store = ShardedRowStore(RowStore(d, device=local), rank, world, device=dev, exchange=mode)
 store.add_local(corpus[lo:hi], None, doc_base=lo)
-doc, row, score = store.search(q, 10)
+for _ in range(3):                              # repeated calls: exchange parity / epoch bookkeeping
+    doc, row, score = store.search(q, 10)
+if rank == 0:
+    print("exchange mode:", store.mode, flush=True)
 ok = True
 if rank == 0:
     build.build_oracle()

@@ -220,7 +220,7 @@ sys.path.insert(0, os.environ["REPO_ROOT"])
 from marqo_b200 import build
 build.build_oracle()
 from oracle import score_oracle as so
-from marqo_b200.distributed import allgather_topk, shard_bounds
+from marqo_b200.distributed import ShardedRowStore, allgather_topk, shard_bounds
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{os.environ['MASTER_PORT']}", rank=rank, world_size=world)
 rng = np.random.default_rng(0)
@@ -234,6 +234,20 @@ md, mr, ms = allgather_topk(d, r, s)
 ed, er, es = so.search(q, corpus, 6, "dotproduct")
 assert (md == ed).all() and (mr == er).all() and (ms == es).all(), (rank, md, ed)
 assert md[0, 0] == 3 and md[0, 1] == 1500
+# the same through ShardedRowStore (host exchange mode: ONE packed all-gather per query block)
+class _Store:
+    dim = 64
+    def __init__(self, rows): self.rows, self.off = rows, 0
+    def set_doc_offset(self, o): self.off = o
+    def add(self, v, ids): pass
+    def search(self, q, k):
+        d, r, s = so.search(q, self.rows, k, "dotproduct")
+        return np.where(d >= 0, d + self.off, -1), r, s
+sh = ShardedRowStore(_Store(corpus[lo:hi]), rank, world)
+assert sh.mode == "host"
+sh.add_local(None, None, lo)
+sd, sr, ss = sh.search(q, 6)
+assert (sd == ed).all() and (ss == es).all()
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

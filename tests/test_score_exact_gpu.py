@@ -340,3 +340,20 @@ def test_two_million_rows_768(gpu_required, score_oracle):
     d100, _, _ = store.search(q, 100)
     e100, _, _ = score_oracle.search_half(qh, host.view(np.uint16), 100)
     np.testing.assert_array_equal(d100, e100)
+
+
+def test_row_sharded_search_two_gpus(gpu_required):
+    """N = 2 data path under torchrun: row shards, fused peer-store exchange (falls back to NCCL all-gather), identical
+    merged result on both ranks, ids bit-exact vs the oracle (tests/dist_check_multigpu.py).  Needs 2 GPUs."""
+    import os
+    import subprocess
+    import sys
+    from marqo_b200 import _native
+    if _native.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under `gpurun --gpus 2`)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "dist_check_multigpu.py")]
+    r = subprocess.run(cmd, cwd=root, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "ids bit-exact vs oracle: True" in r.stdout and "all ranks identical: True" in r.stdout
