@@ -353,6 +353,25 @@ int b200_interpolate_vectors(const double* vecs, const double* weights, int n, i
                              int* out_error_kind);
 
 /* ===================================================================================== */
+/* Image decode: baseline JPEG -> uint8 HWC RGB on the GPU.               */
+/* Replaces the Pillow decode on Marqo's download threads (Image.open at                  */
+/* src/marqo/core/inference/image_download.py:146-152, pixels materialised by the         */
+/* transform at src/marqo/tensor_search/add_docs.py:129-134).  Huffman decoding runs on   */
+/* the host (images of a batch in parallel); dequantisation + integer IDCT, fancy chroma  */
+/* upsampling and YCbCr -> RGB run in two CUDA kernels over the whole batch and reproduce */
+/* libjpeg-turbo's default decode (what Pillow returns) bit for bit.                      */
+/* ===================================================================================== */
+
+/* Size of a JPEG and whether this decoder handles it (baseline / extended-sequential Huffman, 8-bit, grey or YCbCr
+ * with 4:4:4 / 4:2:2 / 4:2:0 sampling).  *out_supported == 0: decode it with Pillow (b200_last_error says why). */
+int b200_jpeg_info(const uint8_t* file, size_t nbytes, int32_t* out_height, int32_t* out_width, int32_t* out_supported);
+/* Decode n files.  d_out[i]: device buffer of heights[i] * widths[i] * 3 bytes on `device` (sizes from b200_jpeg_info, or
+ * from a first call with d_out[i] == NULL, which only fills heights / widths / status).  status[i]: B200_OK,
+ * B200_ERR_UNSUPPORTED (fall back to Pillow for this image) or B200_ERR_INVALID_ARG (no output buffer).  Synchronous. */
+int b200_jpeg_decode_batch(int device, const uint8_t* const* files, const size_t* nbytes, int n, uint8_t* const* d_out,
+                           int32_t* heights, int32_t* widths, int32_t* status);
+
+/* ===================================================================================== */
 /* Diagnostics: run ONE kernel of the encoder on host data (used by the kernel-level     */
 /* numerics tests; not part of the reference-facing surface).                            */
 /* ===================================================================================== */
@@ -371,6 +390,10 @@ int b200_debug_attention(int device, const float* qkv, int B, int S, int W, int 
 int b200_debug_attention_time(int device, int B, int S, int W, int H, int mask, int iters, float* out_ms);
 int b200_debug_layernorm(int device, const float* x, const float* gamma, const float* beta, float eps, int rows, int w,
                          float* out);
+/* The JPEG decoder's arithmetic (shared __host__ __device__ code of the two kernels) run on the host: lets the CPU test
+ * suite pin it against Pillow pixel for pixel.  A test hook, not a product path.  out_rgb == NULL: size query. */
+int b200_debug_jpeg_decode_host(const uint8_t* file, size_t nbytes, uint8_t* out_rgb, size_t out_capacity,
+                                int32_t* out_height, int32_t* out_width);
 /* Pillow-compatible bicubic resize (shortest side -> S) + centre crop of uint8 HWC images [n,h,w,3] -> [n,S,S,3]. */
 int b200_debug_resize(int device, const uint8_t* hwc, int n, int h, int w, int S, uint8_t* out);
 

@@ -49,8 +49,18 @@ class _PreprocessToU8:
     thread; here the thread only hands the decoded pixels over as a uint8 HWC tensor and the whole transform runs on
     the GPU fused into the patch-embed load."""
 
+    def __init__(self, gpu_decode: bool = True):
+        self.gpu_decode = gpu_decode
+
     def __call__(self, pil_image):
         import torch
+        if self.gpu_decode:
+            # Image.open() is lazy: a JPEG that has not been decoded yet is handed over still encoded and decoded on
+            # the GPU with the rest of its batch (image_decode.py, b200_jpeg_decode_batch — bit-exact with Pillow)
+            from .image_decode import EncodedImage, encoded_bytes_of
+            data = encoded_bytes_of(pil_image)
+            if data is not None:
+                return EncodedImage(data, "JPEG")
         return torch.from_numpy(np.asarray(pil_image.convert("RGB"), dtype=np.uint8).copy())
 
 
@@ -124,6 +134,18 @@ class B200OpenCLIP:
         if len(items) == 0:
             raise UnidentifiedImageError("received empty list, expected at least one element.")
         S = self.model.image_size
+        from .image_decode import EncodedImage, decode_images_to_device
+        if any(isinstance(it, (EncodedImage, bytes, bytearray)) for it in items):
+            # still-encoded files (what the preprocessor hands over for JPEGs): decode the batch on the GPU; the pixels
+            # stay in HBM for the resize + patch-embed kernels
+            enc_idx = [i for i, it in enumerate(items) if isinstance(it, (EncodedImage, bytes, bytearray))]
+            try:
+                decoded = decode_images_to_device([items[i] for i in enc_idx], device=self.model.device)
+            except OSError as e:              # Pillow's error for broken files, wrapped like the reference does
+                raise UnidentifiedImageError(str(e)) from e
+            items = list(items)
+            for i, t in zip(enc_idx, decoded):
+                items[i] = t
         if all(self._on_model_device(it) for it in items):
             return self._encode_device_images(items, bool(normalize))
         u8, f32 = [], []

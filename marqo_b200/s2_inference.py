@@ -465,6 +465,8 @@ def _is_image(inputs) -> bool:
         return _looks_like_url(thing)
     if isinstance(thing, np.ndarray) or _is_tensor(thing) or type(thing).__module__.startswith("PIL."):
         return True
+    if type(thing).__name__ == "EncodedImage":   # extension: a still-encoded image from this engine's own preprocessor
+        return True                              # (marqo_b200/image_decode.py), decoded on the GPU by encode_image
     raise UnidentifiedImageError(f"expected type Image or str for inputs but received type {type(thing)}")
 
 

@@ -237,3 +237,34 @@ def test_concurrent_encode_calls_are_serialised_per_handle(gpu_required):
     for a, b in zip(serial, out):
         np.testing.assert_array_equal(a, b)          # same kernels, same order of arithmetic -> bitwise equal
     enc.close()
+
+
+def test_vectorise_decodes_jpegs_on_the_gpu(gpu_required, monkeypatch):
+    """The ingest seam end to end: lazy PIL images (Image.open, image_download.py:146-152) -> model.preprocess hands the
+    still-encoded JPEG over -> vectorise() -> encode_image decodes the batch on the GPU (bit-exact with Pillow), resizes
+    and encodes.  Same vectors as handing over Pillow-decoded pixels; a progressive file rides along through Pillow."""
+    import io
+    from PIL import Image
+    from marqo_b200 import s2_inference as S2
+    from marqo_b200.image_decode import EncodedImage
+    rng = np.random.default_rng(4)
+    files = []
+    for i, (h, w) in enumerate([(300, 400), (224, 224), (500, 333), (300, 400)]):
+        img = Image.fromarray(np.kron(rng.integers(0, 256, size=(h // 20 + 1, w // 20 + 1, 3), dtype=np.uint8),
+                                      np.ones((20, 20, 1), np.uint8))[:h, :w])
+        b = io.BytesIO()
+        img.save(b, format="JPEG", quality=85, subsampling=(0, 1, 2, 2)[i], progressive=(i == 3))
+        files.append(b.getvalue())
+    props = {"name": "tiny-clip", "dimensions": 128, "type": "open_clip", "arch": TINY_CLIP_ARCH, "random_init": 5,
+             "max_batch": 8}
+    S2.clear_loaded_models()
+    pre = S2.load_multimodal_model_and_get_preprocessors("tiny-clip", props, device="cuda:0")[1]["image"]
+    media = [pre(Image.open(io.BytesIO(f))).to("cuda:0") for f in files]
+    assert all(isinstance(m, EncodedImage) for m in media[:3])
+    got = np.asarray(S2.vectorise("tiny-clip", media, model_properties=props, device="cuda:0", normalize_embeddings=True,
+                                  modality=S2.Modality.IMAGE))
+    decoded = [np.asarray(Image.open(io.BytesIO(f)).convert("RGB")) for f in files]
+    want = np.asarray(S2.vectorise("tiny-clip", [torch.from_numpy(d) for d in decoded], model_properties=props,
+                                   device="cuda:0", normalize_embeddings=True, modality=S2.Modality.IMAGE))
+    np.testing.assert_array_equal(got, want)          # identical pixels -> identical kernels -> identical vectors
+    S2.clear_loaded_models()

@@ -58,10 +58,24 @@ def test_many_identical_rows_with_permuted_documents(gpu_required, score_oracle)
     doc, _, score = _check(store, score_oracle, q, corpus, 10, doc_of_row=doc_of_row)
     assert list(doc[0]) == sorted(doc_of_row[dup_rows])[:10]
     assert np.all(score[0] == score[0, 0])
-    st = store.search_stats()
-    assert st["flagged"] >= 1 and st["collect_passes"] >= 1      # the guard noticed; the fallback answered
+    # 40 ties still fit the 64 candidates the merge re-scores exactly: answered in one pass, provably (guard held)
+    assert store.search_stats()["flagged"] == 0
     for k in (1, 16, 39, 40, 41, 64):
         _check(store, score_oracle, q, corpus, k, doc_of_row=doc_of_row)
+    # 150 ties do not: the guard must notice (exact k-th key == bound of the unexamined rows) and the collect pass answer
+    more = rng.choice(n, size=150, replace=False)
+    corpus2 = corpus.copy()
+    corpus2[more] = corpus2[more[0]]
+    q2 = q.copy()
+    q2[0] = corpus2[more[0]]
+    store2 = RowStore(d)
+    store2.add(corpus2, doc_of_row)
+    doc2, _, _ = _check(store2, score_oracle, q2, corpus2, 10, doc_of_row=doc_of_row)
+    assert list(doc2[0]) == sorted(doc_of_row[more])[:10]
+    st = store2.search_stats()
+    assert st["flagged"] >= 1 and st["collect_passes"] >= 1
+    for k in (64, 100, 149, 150, 151):
+        _check(store2, score_oracle, q2, corpus2, k, doc_of_row=doc_of_row)
 
 
 @pytest.mark.parametrize("spread", ["one_tile", "all_over"])

@@ -467,3 +467,56 @@ def test_index_scenarios_on_the_cpu_stand_in(monkeypatch):
     monkeypatch.setattr(gti, "RowStore", _Store)
     run_feed_query_scenario()
     run_score_modifier_scenario()
+
+
+def test_device_chunks_feed_coalesces_into_one_append(monkeypatch):
+    """add_documents fast path host logic: DeviceChunks of one batch that are consecutive in device memory become ONE
+    row append per tensor field; mixed host / device documents keep feed order; rejected documents leave no rows."""
+    import numpy as np
+    import marqo_b200.gpu_tensor_index as gti
+    from marqo_b200.gpu_tensor_index import DeviceChunks
+    from _filter_scenario import _doc, _yql
+
+    class _DevStore(_NumpyRowStore):
+        """'device memory' = a dict of fake pointers -> numpy rows"""
+        heap = {}
+        calls = []
+
+        def add_device_docs(self, ptr, doc_ids):
+            base, off = max((b, ptr - b) for b in self.heap if b <= ptr)
+            rows = self.heap[base][off // (self.dim * 4):][:len(doc_ids)]
+            assert len(rows) == len(doc_ids)
+            type(self).calls.append(len(doc_ids))
+            self.add(rows, doc_ids)
+
+    monkeypatch.setattr(gti, "RowStore", _DevStore)
+    rng = np.random.default_rng(9)
+    dim = 64
+    emb = rng.standard_normal((6, dim)).astype(np.float32)
+    emb /= np.linalg.norm(emb, axis=1, keepdims=True)
+    _DevStore.heap = {1 << 20: emb}
+    _DevStore.calls = []
+    ix = gti.GpuTensorIndex()
+    batch = [{"id": f"d{i}", "fields": {"marqo__id": f"d{i}", "n": i,
+                                       "marqo__embeddings_img": DeviceChunks(["0"], (1 << 20) + i * dim * 4, dim, emb)}}
+             for i in range(4)]
+    batch.append({"id": "two", "fields": {"marqo__id": "two",
+                                         "marqo__embeddings_img": DeviceChunks(["0", "1"], (1 << 20) + 4 * dim * 4, dim, emb)}})
+    r = ix.feed_batch(batch, "s1")
+    assert not r.errors and _DevStore.calls == [6]                    # ONE device append for the whole batch
+    res = ix.query(_yql("s1", ["img"], 2), hits=2, ranking="embedding_similarity", model_restrict="s1",
+                   query_features={"marqo__query_embedding": emb[5].tolist()})
+    assert res.hits[0].id.endswith("::two")
+    assert res.hits[0].dict()["fields"]["matchfeatures"]["closest(marqo__embeddings_img)"]["cells"] == {"1": 1.0}
+    # wrong dimension on the device path is rejected up front, like a host document
+    bad = ix.feed_batch([{"id": "bad", "fields": {"marqo__embeddings_img": DeviceChunks(["0"], 1 << 20, 128, emb)}}], "s1")
+    assert bad.errors and bad.responses[0].status == 400 and ix.get_document_count("s1") == 5
+    # host and device documents interleaved: rows stay in feed order
+    _DevStore.calls = []
+    mixed = [_doc("h1", {"marqo__id": "h1"}, {"img": (["c"], emb[0:1])}),
+             {"id": "g1", "fields": {"marqo__id": "g1", "marqo__embeddings_img": DeviceChunks(["0"], (1 << 20) + dim * 4, dim, emb)}},
+             _doc("h2", {"marqo__id": "h2"}, {"img": (["c"], emb[2:3])})]
+    assert not ix.feed_batch(mixed, "s1").errors
+    s = ix._schemas["s1"]
+    order = [s.doc_ids[n] for n, _ in s.row_chunk["marqo__embeddings_img"][-3:]]
+    assert order == ["h1", "g1", "h2"] and _DevStore.calls == [1]
