@@ -17,6 +17,7 @@
 // against the K / V tiles while they sit in shared memory.
 // 113 KB smem + 256 TMEM columns per CTA -> two CTAs per SM, so one CTA's softmax overlaps the other's MMAs.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "attention.cuh"
@@ -43,6 +44,7 @@ constexpr uint32_t SMEM_BYTES =
 static_assert(SMEM_BYTES <= 115712, "two CTAs per SM");
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t S_COL = 0, O_COL = 128;
+constexpr int DEFAULT_SOFTMAX_MODE = 1;
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -79,6 +81,48 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                  :
                  : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_wait_regs16(uint32_t (&v)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+
+// 16 keys (block-local columns k0 .. k0 + 15) of a score row with FOUR independent sum / max chains: the softmax warps
+// are latency-bound (two of them per scheduler), so the serial `lsum += p` chain of the 32-key version below costs
+// more than its instructions.
+template <bool FULL>
+__device__ __forceinline__ void softmax_half_chunk(const uint32_t (&v)[16], int k0, int klo, int khi, float scale_log2e,
+                                                   float m_safe, float (&ls)[4], float (&mx)[4], uint8_t* sP, int r) {
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+        const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
+        float p0, p1;
+        const int a = (i >> 1) & 3;
+        if (FULL) {
+            mx[a] = fmaxf(mx[a], fmaxf(s0, s1));
+            p0 = ex2(fmaf(s0, scale_log2e, -m_safe));
+            p1 = ex2(fmaf(s1, scale_log2e, -m_safe));
+        } else {
+            const int kk = k0 + i;
+            const bool ok0 = kk >= klo && kk < khi, ok1 = kk + 1 >= klo && kk + 1 < khi;
+            mx[a] = ok0 ? fmaxf(mx[a], s0) : mx[a];
+            mx[a] = ok1 ? fmaxf(mx[a], s1) : mx[a];
+            p0 = ok0 ? ex2(fmaf(s0, scale_log2e, -m_safe)) : 0.f;
+            p1 = ok1 ? ex2(fmaf(s1, scale_log2e, -m_safe)) : 0.f;
+        }
+        ls[a] += p0 + p1;
+        pk[i >> 1] = pack2(p0, p1);
+    }
+    // keys k0 .. k0+15 -> 64-key chunk (k0 >> 6), 16-byte units ((k0 & 63) >> 3) and the next one, of row r
+    uint8_t* rowp = sP + (size_t)(k0 >> 6) * (BQ * 128) + (size_t)r * 128;
+    const int unit = (k0 & 63) >> 3;
+    *reinterpret_cast<uint4*>(rowp + ((unit ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(rowp + (((unit + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
 // One 32-key chunk of a score row: p = exp2(s * scale - m_safe) for the keys in [klo, khi) (block-local indices), 0 for
@@ -150,10 +194,13 @@ __device__ __forceinline__ void item_extent(const Item& w, int S, int s_main, co
     nkb = (kend + BKV - 1) / BKV;
 }
 
-// 224 threads x 144 registers x 2 CTAs = 64512 of the SM's 65536 registers: __launch_bounds__(224, 2) would make ptxas
-// budget for 256-thread CTAs (128 registers) and spill the prefetched score chunk.
-template <int MASK, bool PACKED>
-__global__ void __maxnreg__(144)
+// Two CTAs per SM: 14 warps over 4 schedulers put 4 warps on one of them, and a scheduler's register partition
+// (16384 registers) holds 4 warps only up to 128 registers each — a 144-register build (tried in round 2) silently
+// dropped to ONE CTA per SM and ran 1.85x slower.
+// SM: softmax schedule of the row threads — 0 two passes over S (exact block maximum), 1 one pass / one register buffer,
+// 2 one pass with the next chunk's tcgen05.ld in flight (two buffers).  All three use the lazy exponent reference.
+template <int MASK, bool PACKED, int SM>
+__global__ void __launch_bounds__(THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ qkv,
                     __nv_bfloat16* __restrict__ out, int S, int W, int H, const int32_t* __restrict__ kv_len,
                     float scale_log2e, int s_main, int inline_tail_rows, int q_blocks, int total_items, int pack, int B) {
@@ -568,80 +615,127 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                     khi = p_hi;
                 }
                 const bool full = klo <= 0 && khi >= BKV;
-                // ONE pass over the scores (the two-pass version read S twice from TMEM and waited for each of its eight
-                // loads).  The exponent reference m_ref is NOT the exact block maximum: it is the running reference of
-                // the row (first block: the maximum of the row's first 32 scores), so later blocks need no rescale of
-                // O at all.  The exact maximum is tracked on the side; only if it exceeds the reference by more than
-                // 2^8 (P would outgrow bf16's useful range / risk overflow) the warp falls back to the exact two-pass
-                // update below.  exp2(s - m_ref) <= 256, sums stay far inside fp32.
-                uint32_t va[32], vb[32];
-                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL, va);
-                tmem_ld_wait_regs(va);
-                float m_ref = m_run;
-                if (j == 0) {
-                    float c0 = -INFINITY;
+                // The exponent reference of a row is LAZY: it only moves when the block's true maximum exceeds it by
+                // more than 2^8 (exp2(s - ref) <= 256 keeps P inside bf16's useful range and every sum far inside
+                // fp32), so after a row's first block the O accumulator is almost never rescaled.  All decisions are
+                // warp-uniform (__any_sync): tcgen05.ld / st are warp-collective.
+                float lsum = 0.f, mx = -INFINITY, alpha = 1.f, m_new = m_run;
+                uint32_t va[32];
+                if (SM == 0) {
+                    // ---- two passes over S in TMEM: exact block maximum first, then exp / sum / P
+#pragma unroll 1
+                    for (int c = 0; c < BKV / 32; ++c) {
+                        ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, va);
+                        tmem_ld_wait_regs(va);
+                        if (full) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (full || (i >= klo && i < khi)) c0 = fmaxf(c0, __uint_as_float(va[i]));
-                    m_ref = c0 * scale_log2e;   // scale > 0: max commutes with the scaling
-                }
-                const float m_safe = m_ref == -INFINITY ? 0.f : m_ref;
-                // P buffer and O accumulator are free again (the previous item's last PV was awaited in its epilogue)
-                if (j > 0) ptx::mbar_wait(pv_done, par ^ 1);
-                float lsum = 0.f, mx = -INFINITY;
-                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 32, vb);      // chunk c + 1 is in flight while chunk c is
-                if (full) softmax_chunk<true>(va, 0, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);   // processed
-                else softmax_chunk<false>(va, 0, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
-                tmem_ld_wait_regs(vb);
-                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 64, va);
-                if (full) softmax_chunk<true>(vb, 1, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
-                else softmax_chunk<false>(vb, 1, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
-                tmem_ld_wait_regs(va);
-                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 96, vb);
-                if (full) softmax_chunk<true>(va, 2, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
-                else softmax_chunk<false>(va, 2, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
-                tmem_ld_wait_regs(vb);
-                if (full) softmax_chunk<true>(vb, 3, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
-                else softmax_chunk<false>(vb, 3, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
-                float alpha = 1.f;
-                float m_new = m_ref;
-                const float m_true = fmaxf(m_ref, mx * scale_log2e);
-                const bool exceeded = m_true > m_safe + 8.0f;
-                if (__any_sync(0xffffffffu, exceeded)) {   // warp-uniform: tcgen05.ld / st are warp-collective
-                    // exact update for this block: reference = true running maximum, P recomputed, O rescaled
-                    m_new = m_true;
-                    const float ms2 = m_new == -INFINITY ? 0.f : m_new;
-                    alpha = ex2(m_run - ms2);   // 0 on the first block; 1 for rows whose maximum did not move
-                    lsum = 0.f;
+                            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(va[i]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (c * 32 + i >= klo && c * 32 + i < khi) mx = fmaxf(mx, __uint_as_float(va[i]));
+                        }
+                    }
+                    const float bmax = mx * scale_log2e;   // scale > 0: max commutes with the scaling
+                    const bool move = j == 0 || bmax > m_run + 8.0f;
+                    if (move) m_new = fmaxf(m_run, bmax);
+                    const float m_safe = m_new == -INFINITY ? 0.f : m_new;
+                    if (move) alpha = ex2(m_run - m_safe);   // 0 on the first block
+                    if (j > 0) ptx::mbar_wait(pv_done, par ^ 1);   // P buffer and O accumulator are free again
                     float dummy = -INFINITY;
 #pragma unroll 1
                     for (int c = 0; c < BKV / 32; ++c) {
                         ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, va);
                         tmem_ld_wait_regs(va);
-                        if (full) softmax_chunk<true>(va, c, klo, khi, scale_log2e, ms2, lsum, dummy, sP, r);
-                        else softmax_chunk<false>(va, c, klo, khi, scale_log2e, ms2, lsum, dummy, sP, r);
+                        if (full) softmax_chunk<true>(va, c, klo, khi, scale_log2e, m_safe, lsum, dummy, sP, r);
+                        else softmax_chunk<false>(va, c, klo, khi, scale_log2e, m_safe, lsum, dummy, sP, r);
                     }
-                    if (j > 0) {
-                        // rescale the running output by alpha (thread-local: lane == row)
-#pragma unroll 1
-                        for (int c = 0; c < HD / 32; ++c) {
-                            ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + c * 32, va);
-                            tmem_ld_wait_regs(va);
+                } else {
+                    // ---- one pass: reference = running reference (first block: max of the row's first 32 scores);
+                    //      the exact maximum is tracked on the side and only checked afterwards
+                    ptx::tmem_ld_32x32b_x32(lane_addr + S_COL, va);
+                    tmem_ld_wait_regs(va);
+                    float m_ref = m_run;
+                    if (j == 0) {
+                        float c0 = -INFINITY;
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) * alpha);
-                            ptx::tmem_st_32x32b_x32(lane_addr + O_COL + c * 32, va);
+                        for (int i = 0; i < 32; ++i)
+                            if (full || (i >= klo && i < khi)) c0 = fmaxf(c0, __uint_as_float(va[i]));
+                        m_ref = c0 * scale_log2e;
+                    }
+                    const float m_safe = m_ref == -INFINITY ? 0.f : m_ref;
+                    if (j > 0) ptx::mbar_wait(pv_done, par ^ 1);
+                    if (SM == 2) {
+                        // 16-column half chunks through two 16-register buffers inside ONE loop body: the next half's
+                        // tcgen05.ld is in flight while this half is exponentiated (same code size and registers as the
+                        // 32-column version; the round-2 attempt with two 32-register buffers and an unrolled body lost
+                        // more to instruction fetch than it hid)
+                        uint32_t vb[16], vlo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) vlo[i] = va[i];   // columns 0-15 are already here (reference pass)
+                        float ls4[4] = {0.f, 0.f, 0.f, 0.f}, mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 1
+                        for (int c = 0; c < BKV / 32; ++c) {
+                            if (c > 0) tmem_ld_wait_regs16(vlo);
+                            ptx::tmem_ld_32x32b_x16(lane_addr + S_COL + c * 32 + 16, vb);
+                            if (full) softmax_half_chunk<true>(vlo, c * 32, klo, khi, scale_log2e, m_safe, ls4, mx4, sP, r);
+                            else softmax_half_chunk<false>(vlo, c * 32, klo, khi, scale_log2e, m_safe, ls4, mx4, sP, r);
+                            tmem_ld_wait_regs16(vb);
+                            if (c + 1 < BKV / 32) ptx::tmem_ld_32x32b_x16(lane_addr + S_COL + (c + 1) * 32, vlo);
+                            if (full) softmax_half_chunk<true>(vb, c * 32 + 16, klo, khi, scale_log2e, m_safe, ls4, mx4, sP, r);
+                            else softmax_half_chunk<false>(vb, c * 32 + 16, klo, khi, scale_log2e, m_safe, ls4, mx4, sP, r);
                         }
-                        ptx::tmem_st_wait();
-                    } else {
-                        alpha = 0.f;   // nothing accumulated yet (l_run == 0)
+                        lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+                        mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                    } else {         // SM == 1: one buffer, one loop body
+#pragma unroll 1
+                        for (int c = 0; c < BKV / 32; ++c) {
+                            if (c > 0) {
+                                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, va);
+                                tmem_ld_wait_regs(va);
+                            }
+                            if (full) softmax_chunk<true>(va, c, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                            else softmax_chunk<false>(va, c, klo, khi, scale_log2e, m_safe, lsum, mx, sP, r);
+                        }
+                    }
+                    m_new = m_ref;
+                    const float m_true = fmaxf(m_ref, mx * scale_log2e);
+                    const bool exceeded = m_true > m_safe + 8.0f;
+                    if (__any_sync(0xffffffffu, exceeded)) {
+                        // exact update for this block: reference = true running maximum, P recomputed
+                        m_new = m_true;
+                        const float ms2 = m_new == -INFINITY ? 0.f : m_new;
+                        alpha = ex2(m_run - ms2);   // 0 on the first block; 1 for rows whose reference did not move
+                        lsum = 0.f;
+                        float dummy = -INFINITY;
+#pragma unroll 1
+                        for (int c = 0; c < BKV / 32; ++c) {
+                            ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + c * 32, va);
+                            tmem_ld_wait_regs(va);
+                            if (full) softmax_chunk<true>(va, c, klo, khi, scale_log2e, ms2, lsum, dummy, sP, r);
+                            else softmax_chunk<false>(va, c, klo, khi, scale_log2e, ms2, lsum, dummy, sP, r);
+                        }
                     }
                 }
+                if (j == 0) alpha = 0.f;   // nothing accumulated yet (l_run == 0, O is overwritten by the first PV)
                 l_run = l_run * alpha + lsum;
                 m_run = m_new;
                 // S has been consumed: the MMA warp may overwrite it with the next block's scores
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(s_free);
+                if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+                    // rescale the running output by alpha (thread-local: lane == row)
+#pragma unroll 1
+                    for (int c = 0; c < HD / 32; ++c) {
+                        ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + c * 32, va);
+                        tmem_ld_wait_regs(va);
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) va[i] = __float_as_uint(__uint_as_float(va[i]) * alpha);
+                        ptx::tmem_st_32x32b_x32(lane_addr + O_COL + c * 32, va);
+                    }
+                    ptx::tmem_st_wait();
+                }
                 ptx::fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the tensor core's async proxy
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -730,19 +824,45 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
 
 }  // namespace tc
 
+using KernelFn = void (*)(const CUtensorMap, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, const int32_t*, float,
+                          int, int, int, int, int, int);
+
+template <int SM>
+static KernelFn kernel_for(int mask, bool packed) {
+    static const KernelFn table[2][3] = {
+        {tc::attention_tc_kernel<MASK_NONE, false, SM>, tc::attention_tc_kernel<MASK_CAUSAL, false, SM>,
+         tc::attention_tc_kernel<MASK_KEYLEN, false, SM>},
+        {tc::attention_tc_kernel<MASK_NONE, true, SM>, tc::attention_tc_kernel<MASK_CAUSAL, true, SM>,
+         tc::attention_tc_kernel<MASK_KEYLEN, true, SM>}};
+    return table[packed ? 1 : 0][mask];
+}
+
+static KernelFn pick_kernel(int sm, int mask, bool packed) {
+    switch (sm) {
+        case 0: return kernel_for<0>(mask, packed);
+        case 2: return kernel_for<2>(mask, packed);
+        default: return kernel_for<1>(mask, packed);
+    }
+}
+
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
               cudaStream_t stream) {
     if (B <= 0 || S <= 0) return 0;
     if (W != H * tc::HD) fail(B200_ERR_UNSUPPORTED, "attention: head_dim must be 64 (width %d, heads %d)", W, H);
+    if (mask < MASK_NONE || mask > MASK_KEYLEN) fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);
+    if (mask == MASK_KEYLEN && !kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
+    // softmax schedule (see the kernel's SM parameter); MARQO_B200_ATTN_SOFTMAX=0|1|2 overrides for A/B timing
+    static const int softmax_mode = [] {
+        const char* e = getenv("MARQO_B200_ATTN_SOFTMAX");
+        return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : tc::DEFAULT_SOFTMAX_MODE;
+    }();
     static std::once_flag once;
     std::call_once(once, [] {
-        const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_NONE, false>, attr, (int)tc::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_CAUSAL, false>, attr, (int)tc::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_KEYLEN, false>, attr, (int)tc::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_NONE, true>, attr, (int)tc::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_CAUSAL, true>, attr, (int)tc::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(tc::attention_tc_kernel<MASK_KEYLEN, true>, attr, (int)tc::SMEM_BYTES));
+        for (int sm = 0; sm < 3; ++sm)
+            for (int pk = 0; pk < 2; ++pk)
+                for (int mk = 0; mk < 3; ++mk)
+                    MB_CUDA(cudaFuncSetAttribute(pick_kernel(sm, mk, pk != 0), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)tc::SMEM_BYTES));
     });
     // one tensor map over the packed [B*S, 3W] matrix serves Q, K and V tiles (64 columns x 128 rows, 128B swizzle);
     // rows past the end of the matrix are zero-filled, rows of the next sequence are masked by key index
@@ -758,24 +878,8 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
         const int groups = (B + pack - 1) / pack;
         const int total_items = groups * H;
         const int grid = std::min(2 * sm_count(device), total_items);
-        auto run = [&](auto kern) {
-            kern<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, H, kv_len, scale_log2e,
-                                                              /*s_main=*/1 << 30, 0, /*q_blocks=*/1, total_items, pack, B);
-        };
-        switch (mask) {
-            case MASK_NONE:
-                run(tc::attention_tc_kernel<MASK_NONE, true>);
-                break;
-            case MASK_CAUSAL:
-                run(tc::attention_tc_kernel<MASK_CAUSAL, true>);
-                break;
-            case MASK_KEYLEN:
-                if (!kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
-                run(tc::attention_tc_kernel<MASK_KEYLEN, true>);
-                break;
-            default:
-                fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);
-        }
+        pick_kernel(softmax_mode, mask, true)<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(
+            tmap, qkv, out, S, W, H, kv_len, scale_log2e, /*s_main=*/1 << 30, 0, /*q_blocks=*/1, total_items, pack, B);
         MB_CUDA(cudaGetLastError());
         return 1;
     }
@@ -792,24 +896,8 @@ int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     int grid = 2 * sm_count(device);
     if ((q_blocks & 1) == 0 && (grid & 1) == 0) grid -= 1;
     grid = std::min(grid, total_items);
-    auto run = [&](auto kern) {
-        kern<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(tmap, qkv, out, S, W, H, kv_len, scale_log2e, s_main, inline_rows,
-                                                          q_blocks, total_items, 1, B);
-    };
-    switch (mask) {
-        case MASK_NONE:
-            run(tc::attention_tc_kernel<MASK_NONE, false>);
-            break;
-        case MASK_CAUSAL:
-            run(tc::attention_tc_kernel<MASK_CAUSAL, false>);
-            break;
-        case MASK_KEYLEN:
-            if (!kv_len) fail(B200_ERR_INTERNAL, "attention: kv_len required for key-length masking");
-            run(tc::attention_tc_kernel<MASK_KEYLEN, false>);
-            break;
-        default:
-            fail(B200_ERR_INTERNAL, "attention: unknown mask mode %d", mask);
-    }
+    pick_kernel(softmax_mode, mask, false)<<<grid, tc::THREADS, tc::SMEM_BYTES, stream>>>(
+        tmap, qkv, out, S, W, H, kv_len, scale_log2e, s_main, inline_rows, q_blocks, total_items, 1, B);
     MB_CUDA(cudaGetLastError());
     return 1;
 }

