@@ -381,6 +381,20 @@ int b200_jpeg_decode_batch(int device, const uint8_t* const* files, const size_t
  * bf16 before it is returned as fp32. */
 int b200_debug_gemm(int device, const float* A, const float* W, const float* bias, const float* residual, int M, int N,
                     int K, int act, int out_bf16, float* out);
+/* Residual GEMM with the LayerNorm fused into its epilogue (gemm.cuh Epilogue::ln_*): out_x fp32 [M,N] = A W^T + bias
+ * (+ residual); out_ln = LayerNorm(out_x) * gamma + beta rounded to bf16 (returned as fp32).  in_place != 0: the fp32
+ * normalised rows also replace out_x (BERT post-LN).  The launch is repeated `repeats` times on the same strip counters
+ * (they must return to zero); with a residual and in_place == 0 the residual input is never modified, so every
+ * repeat computes the same thing. */
+int b200_debug_gemm_ln(int device, const float* A, const float* W, const float* bias, const float* residual, int M, int N,
+                       int K, const float* gamma, const float* beta, float eps, int in_place, int repeats, float* out_x,
+                       float* out_ln);
+/* ViT patch embedding of uint8 HWC images [n,S,S,3]: ToTensor + Normalize (mean3/std3) -> conv1 (conv_w fp32
+ * [N, 3*patch*patch], no bias) -> token rows: out fp32 [n*(G+1), N], row b*(G+1)+1+i = patch i of image b (+ pos[1+i]
+ * when pos != NULL), class-token rows left zero.  use_gather != 0: the fused gather GEMM (no patch matrix in HBM,
+ * src/marqo/tensor_search/add_docs.py:129-134 folded into the operand load); 0: im2col kernel + plain GEMM. */
+int b200_debug_patch_embed(int device, const uint8_t* hwc, int n, int S, int patch, const float* conv_w, int N,
+                           const float* mean3, const float* std3, const float* pos, int use_gather, float* out);
 /* softmax(q k^T / 8 + mask) v over packed qkv fp32 [B*S, 3*W] (rounded to bf16); mask: 0 none, 1 causal,
  * 2 key length (kv_len int32 [B]).  out fp32 [B*S, W]. */
 int b200_debug_attention(int device, const float* qkv, int B, int S, int W, int H, int mask, const int32_t* kv_len,

@@ -50,6 +50,8 @@ def _digest(paths: list[Path]) -> str:
 
 def build_native(force: bool = False, verbose: bool = False) -> Path:
     """Compile every .cu under csrc/ (one object per file, parallel) and link libmarqo_b200.so."""
+    if not force and os.environ.get("MARQO_B200_USE_PREBUILT") and LIB_PATH.exists():
+        return LIB_PATH   # dev runs on the GPU box: use the library that travelled with the snapshot as it is
     srcs = _sources()
     deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inc")) + [REPO_ROOT / "include" / "marqo_b200.h"]
     stamp = PKG_DIR / "build" / "stamp"

@@ -238,6 +238,7 @@ int launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, in
         const char* e = getenv("MARQO_B200_ATTN_SHORT");
         return e != nullptr && strcmp(e, "mma") == 0;
     }();
+    if (os_supported(S, mask)) return launch_os(qkv, out, B, S, W, H, mask, kv_len, stream);
     if (S >= 128 || !short_on_mma) {
         return launch_tc(qkv, out, B, S, W, H, mask, kv_len, stream);
     }

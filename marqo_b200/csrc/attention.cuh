@@ -20,5 +20,11 @@ int launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, in
 int launch_tc(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
               cudaStream_t stream);
 
+// One-shot kernel for 129 <= S <= 257 (attention_os.cu): all keys in one N = 256 tcgen05.mma, exact two-pass softmax in
+// TMEM, P fed to the P V product straight from TMEM.  mask: MASK_NONE or MASK_KEYLEN.
+bool os_supported(int S, int mask);
+int launch_os(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W, int H, int mask, const int32_t* kv_len,
+              cudaStream_t stream);
+
 }  // namespace attention
 }  // namespace mb

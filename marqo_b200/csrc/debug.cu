@@ -66,6 +66,97 @@ void require_device(int device) {
 
 extern "C" {
 
+int b200_debug_patch_embed(int device, const uint8_t* hwc, int n, int S, int patch, const float* conv_w, int N,
+                           const float* mean3, const float* std3, const float* pos, int use_gather, float* out) {
+    return guarded([&] {
+        MB_CHECK_ARG(hwc && conv_w && mean3 && std3 && out, "NULL buffer");
+        MB_CHECK_ARG(n > 0 && S > 0 && patch > 0 && S % patch == 0 && N > 0 && N % 32 == 0, "bad shape");
+        require_device(device);
+        DeviceGuard g(device);
+        Scratch sc;
+        MB_CUDA(cudaStreamCreate(&sc.s));
+        const int G = (S / patch) * (S / patch), K = 3 * patch * patch;
+        uint8_t* dImg = sc.upload(hwc, (size_t)n * S * S * 3);
+        float* dW = sc.upload(conv_w, (size_t)N * K);
+        float* dOut = sc.alloc<float>((size_t)n * (G + 1) * N);
+        MB_CUDA(cudaMemsetAsync(dOut, 0, (size_t)n * (G + 1) * N * 4, sc.s));
+        gemm::Epilogue ep;
+        ep.out = dOut;
+        ep.ldo = N;
+        ep.out_fp32 = 1;
+        ep.remap_group = G;                                   // token row b * (G + 1) + 1 + i, as the ViT forward does
+        ep.rowbias = pos ? sc.upload(pos, (size_t)(G + 1) * N) : nullptr;
+        if (!pos) ep.rowbias = nullptr;
+        int sms = sm_count(device);
+        if (use_gather) {
+            MB_CHECK_ARG(gemm::patch_gather_supported(S, patch), "the gather GEMM does not support image %d / patch %d", S,
+                         patch);
+            __nv_bfloat16* dWg = sc.alloc<__nv_bfloat16>((size_t)N * gemm::patch_gather_k(patch));
+            kernels::patch_weight_rows(dW, N, patch, gemm::patch_gather_kbpd(patch), dWg, sc.s);
+            gemm::PatchGather pg;
+            pg.img = dImg;
+            pg.n = n;
+            pg.S = S;
+            pg.patch = patch;
+            for (int i = 0; i < 3; ++i) {
+                pg.mean[i] = mean3[i];
+                pg.std[i] = std3[i];
+            }
+            gemm::launch_patch_embed(pg, dWg, N, ep, sms, sc.s);
+        } else {
+            const int kpad = (int)round_up((size_t)K, 64);
+            __nv_bfloat16* dWp = sc.alloc<__nv_bfloat16>((size_t)N * kpad);
+            kernels::pad_rows_to_bf16(dW, N, K, kpad, dWp, sc.s);
+            __nv_bfloat16* dP = sc.alloc<__nv_bfloat16>((size_t)n * G * kpad);
+            kernels::im2col_u8(dImg, n, S, patch, kpad, mean3, std3, dP, sc.s);
+            gemm::launch(dP, kpad, dWp, n * G, N, kpad, ep, sms, sc.s);
+        }
+        MB_CUDA(cudaMemcpyAsync(out, dOut, (size_t)n * (G + 1) * N * 4, cudaMemcpyDeviceToHost, sc.s));
+        MB_CUDA(cudaStreamSynchronize(sc.s));
+    });
+}
+
+int b200_debug_gemm_ln(int device, const float* A, const float* W, const float* bias, const float* residual, int M, int N,
+                       int K, const float* gamma, const float* beta, float eps, int in_place, int repeats, float* out_x,
+                       float* out_ln) {
+    return guarded([&] {
+        MB_CHECK_ARG(A && W && gamma && beta && out_x && out_ln, "NULL buffer");
+        MB_CHECK_ARG(M > 0 && N > 0 && K > 0 && repeats > 0, "M, N, K, repeats must be positive");
+        require_device(device);
+        DeviceGuard g(device);
+        Scratch sc;
+        MB_CUDA(cudaStreamCreate(&sc.s));
+        __nv_bfloat16* dA = sc.upload_bf16(A, (size_t)M * K);
+        __nv_bfloat16* dW = sc.upload_bf16(W, (size_t)N * K);
+        float* dOut = sc.alloc<float>((size_t)M * N);
+        __nv_bfloat16* dLnB = sc.alloc<__nv_bfloat16>((size_t)M * N);
+        float* dLnF = sc.alloc<float>((size_t)M * N);
+        int* dCnt = sc.alloc<int>((size_t)M / 32 + 2);
+        MB_CUDA(cudaMemsetAsync(dCnt, 0, ((size_t)M / 32 + 2) * 4, sc.s));
+        gemm::Epilogue ep;
+        ep.bias = bias ? sc.upload(bias, (size_t)N) : nullptr;
+        ep.residual = residual ? sc.upload(residual, (size_t)M * N) : nullptr;
+        ep.ldr = N;
+        ep.ldo = N;
+        ep.out = dOut;
+        ep.out_fp32 = 1;
+        ep.ln_gamma = sc.upload(gamma, (size_t)N);
+        ep.ln_beta = sc.upload(beta, (size_t)N);
+        ep.ln_eps = eps;
+        ep.ln_out_bf16 = dLnB;
+        ep.ln_out_f32 = in_place ? dOut : nullptr;   // BERT post-LN: the normalised rows replace the fp32 output
+        ep.ln_counters = dCnt;
+        // repeated launches on the same counters: they must come back to zero every time
+        for (int i = 0; i < repeats; ++i) gemm::launch(dA, K, dW, M, N, K, ep, sm_count(device), sc.s);
+        const long long n = (long long)M * N;
+        bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sc.s>>>(dLnB, dLnF, n);
+        MB_CUDA(cudaGetLastError());
+        MB_CUDA(cudaMemcpyAsync(out_x, dOut, (size_t)M * N * 4, cudaMemcpyDeviceToHost, sc.s));
+        MB_CUDA(cudaMemcpyAsync(out_ln, dLnF, (size_t)M * N * 4, cudaMemcpyDeviceToHost, sc.s));
+        MB_CUDA(cudaStreamSynchronize(sc.s));
+    });
+}
+
 int b200_debug_gemm(int device, const float* A, const float* W, const float* bias, const float* residual, int M, int N,
                     int K, int act, int out_bf16, float* out) {
     return guarded([&] {

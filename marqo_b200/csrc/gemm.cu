@@ -24,9 +24,20 @@ constexpr int ACC_STAGES = 2;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;
 constexpr int SMEM_LIMIT = 232448;
 
-template <int BN, int EW>
+// GATHER (ViT patch-embed): the A operand is not a matrix in HBM.  Four extra warps read the uint8 HWC
+// images (whole 16-byte units of the image rows a warp's 32 patches touch, coalesced), stage them in a private smem
+// strip, apply ToTensor + Normalize and write bf16 straight into the 128B-swizzled A stage the tensor core reads;
+// W (one 64-slot k-block group per patch pixel row, zero padded) still arrives by TMA.
+constexpr int GATHER_WARPS = 4;
+constexpr int GATHER_MAX_ROWS = 6;          // image-row strips one warp's 32 consecutive patches can touch (grid >= 7)
+constexpr int GATHER_MAX_ROW_BYTES = 672;   // 3 * 224
+constexpr uint32_t GATHER_WARP_BYTES = 4096;
+static_assert(GATHER_MAX_ROWS * GATHER_MAX_ROW_BYTES <= (int)GATHER_WARP_BYTES, "raw strip buffer");
+
+template <int BN, int EW, bool GATHER = false>
 struct Cfg {
-    static constexpr int THREADS = 64 + 32 * EW;
+    static constexpr int THREADS = 64 + 32 * EW + (GATHER ? 32 * GATHER_WARPS : 0);
+    static constexpr uint32_t RAW_BYTES = GATHER ? GATHER_WARPS * GATHER_WARP_BYTES : 0;
     static constexpr uint32_t B_STAGE_BYTES = (BN / 2) * BK * 2;   // each CTA of the pair holds half of the W tile
     static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     // per epilogue warp: a 32-row transpose buffer (128-byte rows; 64-byte rows for EW = 16) + a 128-byte bias row
@@ -34,9 +45,10 @@ struct Cfg {
     // (EW = 16 keeps the bias row inside the transpose buffer, so the smem ring stays 6 stages deep at BN = 256)
     static constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_ROW_BYTES + (EW == 16 ? 0 : 128);
     static constexpr uint32_t EPI_BYTES = EW * EPI_WARP_BYTES;
-    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - (int)EPI_BYTES) / (int)STAGE_BYTES;
+    static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - (int)EPI_BYTES - (int)RAW_BYTES) / (int)STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-    static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr size_t SMEM_BYTES =
+        (size_t)STAGES * STAGE_BYTES + EPI_BYTES + RAW_BYTES + 1024 /*align*/ + 512 /*barriers*/;
     static constexpr uint32_t TMEM_COLS = ACC_STAGES * BN < 32 ? 32 : ACC_STAGES * BN;
 };
 
@@ -51,6 +63,15 @@ struct Params {
     int tiles_m, tiles_n;   // tiles_m counts 128-row blocks
     int super_m;            // ceil(tiles_m / CLUSTER)
     Epilogue ep;
+    // GATHER only: uint8 HWC images [n, S, S, 3]; A row r = patch r (image r / (g*g), then row-major in the grid)
+    const uint8_t* img;
+    int g;                  // patches per image side
+    int patch;              // patch edge in pixels
+    int row_bytes;          // 3 * S
+    int seg;                // 3 * patch: bytes (= k values) of one patch pixel row
+    int kbpd;               // 64-slot k-blocks per patch pixel row: ceil(seg / 64)
+    int last_steps;         // UMMA_K steps of the last k-block of a pixel row: ceil((seg - 64 (kbpd-1)) / 16)
+    float nscale[3], nshift[3];   // (u8 * nscale[c] + nshift[c]) == (u8/255 - mean[c]) / std[c]
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -90,17 +111,69 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BN, int EW>
-__global__ void __launch_bounds__(64 + 32 * EW, 1)
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// LayerNorm of NR (1 or 2) complete fp32 rows that other SMs may have written: reads bypass L1 (ld.global.cg).
+// Same arithmetic as kernels::ln_row (two-pass mean / variance over the row held in registers).
+template <int NR>
+__device__ __forceinline__ void ln_rows_from_l2(const float* x, int ld, int nv, int w, const Epilogue& ep, long long row0,
+                                                int lane) {
+    float4 v[NR][8];
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nv) v[r][j] = __ldcg(reinterpret_cast<const float4*>(x + (row0 + r) * ld) + lane + 32 * j);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nv) s += v[r][j].x + v[r][j].y + v[r][j].z + v[r][j].w;
+        const float mean = warp_sum(s) / (float)w;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nv) {
+                const float a = v[r][j].x - mean, b = v[r][j].y - mean, c = v[r][j].z - mean, d = v[r][j].w - mean;
+                q += a * a + b * b + c * c + d * d;
+            }
+        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)w + ep.ln_eps);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nv) {
+                const int i4 = lane + 32 * j;
+                const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma) + i4);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_beta) + i4);
+                float4 y;
+                y.x = (v[r][j].x - mean) * rstd * g.x + b.x;
+                y.y = (v[r][j].y - mean) * rstd * g.y + b.y;
+                y.z = (v[r][j].z - mean) * rstd * g.z + b.z;
+                y.w = (v[r][j].w - mean) * rstd * g.w + b.w;
+                if (ep.ln_out_f32) reinterpret_cast<float4*>(ep.ln_out_f32 + (row0 + r) * w)[i4] = y;
+                if (ep.ln_out_bf16)
+                    reinterpret_cast<uint2*>(ep.ln_out_bf16 + (row0 + r) * w)[i4] =
+                        make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+            }
+    }
+}
+
+template <int BN, int EW, bool GATHER>
+__global__ void __launch_bounds__(64 + 32 * EW + (GATHER ? 32 * GATHER_WARPS : 0), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
-    using C = Cfg<BN, EW>;
+    using C = Cfg<BN, EW, GATHER>;
     constexpr int EPI_WARPS = EW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + (size_t)C::STAGES * A_STAGE_BYTES;
     uint8_t* smem_epi = smem + (size_t)C::STAGES * C::STAGE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
+    uint8_t* smem_strip = smem_epi + C::EPI_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_strip + C::RAW_BYTES);
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;
     uint64_t* tempty = tfull + ACC_STAGES;
@@ -118,7 +191,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         ptx::prefetch_tmap(&tmap_a);
         ptx::prefetch_tmap(&tmap_b);
         for (int i = 0; i < C::STAGES; ++i) {
-            ptx::mbar_init(&full[i], CLUSTER);    // leader's copy is used: its own arrive.expect_tx + the peer's arrive
+            // leader's copy is used: its own arrive.expect_tx + the peer's arrive (+ every gather warp of the pair)
+            ptx::mbar_init(&full[i], CLUSTER + (GATHER ? CLUSTER * GATHER_WARPS : 0));
             ptx::mbar_init(&empty[i], 1);         // one multicast tcgen05.commit per use, in each CTA
         }
         for (int i = 0; i < ACC_STAGES; ++i) {
@@ -149,11 +223,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     // completion of BOTH CTAs' loads is tracked by the leader's full barrier
                     const uint32_t leader_full = ptx::mapa_u32(ptx::smem_u32(&full[stage]), 0);
                     if (crank == 0)
-                        ptx::mbar_arrive_expect_tx(&full[stage], CLUSTER * C::STAGE_BYTES);
+                        ptx::mbar_arrive_expect_tx(&full[stage], CLUSTER * (GATHER ? C::B_STAGE_BYTES : C::STAGE_BYTES));
                     else
                         ptx::mbar_arrive_cluster(leader_full);
-                    ptx::tma_load_2d_2sm(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, leader_full, kb * BK, m0,
-                                         ptx::kEvictNormal);
+                    if (!GATHER)
+                        ptx::tma_load_2d_2sm(smem_a + (size_t)stage * A_STAGE_BYTES, &tmap_a, leader_full, kb * BK, m0,
+                                             ptx::kEvictNormal);
                     ptx::tma_load_2d_2sm(smem_b + (size_t)stage * C::B_STAGE_BYTES, &tmap_b, leader_full, kb * BK,
                                          n0 + (int)crank * (BN / CLUSTER), ptx::kEvictLast);
                     if (++stage == C::STAGES) {
@@ -176,10 +251,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 if (lane == 0) {
                     const uint32_t a_base = ptx::smem_u32(smem_a + (size_t)stage * A_STAGE_BYTES);
                     const uint32_t b_base = ptx::smem_u32(smem_b + (size_t)stage * C::B_STAGE_BYTES);
+                    // GATHER: the last k-block of a patch pixel row holds fewer than 64 values; the slots past them are
+                    // never written by the gather warps, so those UMMA_K steps are not issued
+                    const int ksteps = (GATHER && (kb % p.kbpd) == p.kbpd - 1) ? p.last_steps : BK / UMMA_K;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k)
-                        ptx::umma_f16_2sm(tmem_base + acc * BN, ptx::make_desc_k_sw128(a_base + k * UMMA_K * 2),
-                                          ptx::make_desc_k_sw128(b_base + k * UMMA_K * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (k < ksteps)
+                            ptx::umma_f16_2sm(tmem_base + acc * BN, ptx::make_desc_k_sw128(a_base + k * UMMA_K * 2),
+                                              ptx::make_desc_k_sw128(b_base + k * UMMA_K * 2), idesc,
+                                              (kb | k) != 0 ? 1u : 0u);
                     // both CTAs' producers get their stage back; both CTAs' epilogues get the finished accumulator
                     ptx::umma_commit_2sm(&empty[stage], (uint16_t)((1u << CLUSTER) - 1));
                     if (kb == kblocks - 1) ptx::umma_commit_2sm(&tfull[acc], (uint16_t)((1u << CLUSTER) - 1));
@@ -195,7 +275,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
-    } else if (warp >= 2 && EW == 16) {
+    } else if (warp >= 2 && warp < 2 + EW && EW == 16) {
         // ---------------------------------------------------------------- fast bf16 epilogue (16 warps)
         // lane == accumulator row; each warp drains 32 rows x (BN / 4) columns in 32-column chunks:
         // bias -> activation -> bf16 -> 32 x 64 B swizzled staging buffer -> 64-byte coalesced row segments.
@@ -273,7 +353,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 acc_phase ^= 1;
             }
         }
-    } else if (warp >= 2) {
+    } else if (warp >= 2 && warp < 2 + EW) {
         // ---------------------------------------------------------------- epilogue (TMEM -> regs -> smem -> global)
         // A warp may only read the TMEM lanes of sub-partition (warp % 4); the two warps that share a sub-partition
         // split the tile's columns in halves, so 8 warps drain one 128 x BN accumulator.  TMEM hands every lane one ROW
@@ -285,13 +365,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         constexpr int CHUNKS = HALF_COLS / 32;
         const bool has_cols = half * HALF_COLS < BN;  // BN = 32 would leave the second half empty
         const Epilogue& ep = p.ep;
+        const float* const residual = GATHER ? nullptr : ep.residual;   // the patch-embed GEMM has no residual input
         uint8_t* stage_buf = smem_epi + (size_t)(warp - 2) * C::EPI_WARP_BYTES;
         float* bias_row = reinterpret_cast<float*>(stage_buf + 32 * 128);
         const int esz = ep.out_fp32 ? 4 : 2;                  // output element size
         const int cols_per_flush = 128 / esz;                 // 32 fp32 or 64 bf16 columns fill a 128-byte row
         // bf16 results are staged two chunks (64 columns) per flush; a residual block occupies the whole buffer, so
         // residual GEMMs (fp32 out in this engine) flush after every chunk
-        const int chunks_per_flush = (ep.out_fp32 || ep.residual) ? 1 : cols_per_flush / 32;
+        const int chunks_per_flush = (ep.out_fp32 || residual) ? 1 : cols_per_flush / 32;
         const int srow = lane >> 3, sunit = lane & 7;         // coalesced phase: 4 rows x 8 sixteen-byte units per instr
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -299,7 +380,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int m0 = ((t / p.tiles_n) * CLUSTER + (int)crank) * BM;
             const int nt0 = (t % p.tiles_n) * BN + half * HALF_COLS;
             const int wrow0 = m0 + sp * 32;                   // first row of this warp's 32-row band
-            if (ep.residual && has_cols) {
+            if (residual && has_cols) {
                 // pull the residual band this warp needs for its NEXT tile towards L2 (the very first tile: itself)
                 for (int pass = (t == cluster_id ? 0 : 1); pass < 2; ++pass) {
                     const int tn = t + pass * num_clusters;
@@ -307,7 +388,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     const int prow = ((tn / p.tiles_n) * CLUSTER + (int)crank) * BM + sp * 32 + lane;
                     const int pn0 = (tn % p.tiles_n) * BN + half * HALF_COLS;
                     if (prow < p.M) {
-                        const char* r = reinterpret_cast<const char*>(ep.residual + (size_t)prow * ep.ldr + pn0);
+                        const char* r = reinterpret_cast<const char*>(residual + (size_t)prow * ep.ldr + pn0);
 #pragma unroll
                         for (int l = 0; l < HALF_COLS * 4 / 128; ++l)
                             if (pn0 + l * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + l * 128));
@@ -325,11 +406,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 float bias_v = 0.f;
                 if (ep.bias && cols_ok) bias_v = __ldg(ep.bias + n0 + lane);
                 float4 rres[8];
-                if (ep.residual && cols_ok) {
+                if (residual && cols_ok) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int rr = wrow0 + i * 4 + srow;
-                        rres[i] = rr < p.M ? *reinterpret_cast<const float4*>(ep.residual + (size_t)rr * ep.ldr + n0 + sunit * 4)
+                        rres[i] = rr < p.M ? *reinterpret_cast<const float4*>(residual + (size_t)rr * ep.ldr + n0 + sunit * 4)
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
@@ -347,7 +428,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 }
                 if (cols_ok) {
                     bias_row[lane] = bias_v;
-                    if (ep.residual) {
+                    if (residual) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             const int rr = i * 4 + srow;
@@ -381,7 +462,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             f[4 * j + 3] += b.w;
                         }
                     }
-                    if (ep.residual) {
+                    if (residual) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float4 b = *reinterpret_cast<const float4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4));
@@ -434,9 +515,116 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     __syncwarp();
                 }
             }
+            if (!GATHER && ep.ln_gamma != nullptr && has_cols && wrow0 < p.M) {
+                // fused LayerNorm: count the strip's writers and let the last one normalise.  One acq_rel atomic per
+                // warp publishes the whole warp's stores (they are ordered before it by the warp barrier) and, in the
+                // last writer, acquires everybody else's.  NOT __threadfence(): that is fence.sc.gpu, and 16 k
+                // sequentially-consistent fences per launch serialise across the GPU (measured: 33 -> 74 ms per step).
+                __syncwarp();
+                int old = 0;
+                if (lane == 0)
+                    asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;"
+                                 : "=r"(old) : "l"(ep.ln_counters + (wrow0 >> 5)) : "memory");
+                old = __shfl_sync(0xffffffffu, old, 0);
+                if (old == 2 * p.tiles_n - 1) {
+                    if (lane == 0) ep.ln_counters[wrow0 >> 5] = 0;   // ready for the next launch
+                    const float* xo = reinterpret_cast<const float*>(ep.out);
+                    const int nv = p.N >> 7;
+                    const int nrows = min(32, p.M - wrow0);
+                    int rr = 0;
+#pragma unroll 1
+                    for (; rr + 2 <= nrows; rr += 2) ln_rows_from_l2<2>(xo, ep.ldo, nv, p.N, ep, wrow0 + rr, lane);
+                    if (rr < nrows) ln_rows_from_l2<1>(xo, ep.ldo, nv, p.N, ep, wrow0 + rr, lane);
+                }
+            }
             if (++acc == ACC_STAGES) {
                 acc = 0;
                 acc_phase ^= 1;
+            }
+        }
+    } else if (GATHER && warp >= 2 + EW) {
+        // ---------------------------------------------------------------- patch gather (uint8 HWC -> bf16 A stage)
+        // Warp gw owns rows gw*32 .. gw*32+31 of this CTA's 128-row A tile: lane == patch.  Per patch pixel row dy the
+        // warp copies the image-row strips its patches lie on (whole rows of 3*S bytes, 16-byte units, coalesced) into its
+        // private smem strip buffer, then every lane converts its own 3*patch bytes: k = dy*(64*kbpd) + dx*3 + c.
+        const int gw = warp - (2 + EW);
+        uint8_t* strip = smem_strip + (size_t)gw * GATHER_WARP_BYTES;
+        const int r = gw * 32 + lane;                  // row of the A tile
+        const int upr = p.row_bytes >> 4;              // 16-byte units per image row
+        const uint32_t leader_full0 = ptx::mapa_u32(ptx::smem_u32(&full[0]), 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = cluster_id; t < num_super; t += num_clusters) {
+            const int m0 = ((t / p.tiles_n) * CLUSTER + (int)crank) * BM + gw * 32;
+            // patches past M (last tile) are clamped to the last real patch: their rows are computed and never stored
+            const int pfirst = min(m0, p.M - 1), plast = min(m0 + 31, p.M - 1), pl = min(m0 + lane, p.M - 1);
+            const int pr0 = pfirst / p.g;              // global patch-row index = image * g + gy
+            const int prl = pl / p.g;
+            const int nunits = (plast / p.g - pr0 + 1) * upr;
+            const int my_off = (prl - pr0) * p.row_bytes + (pl - prl * p.g) * p.seg;
+            // per lane: up to 8 sixteen-byte units of the strips (offset of the dy = 0 row, in 16-byte units)
+            uint32_t uoff[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int idx = lane + 32 * i;
+                const int rr = idx / upr, uu = idx - rr * upr;
+                const int pr = pr0 + rr;
+                const int b = pr / p.g, gy = pr - b * p.g;
+                uoff[i] = idx < nunits ? (uint32_t)(((size_t)b * (p.g * p.patch) + (size_t)gy * p.patch) * upr + uu) : 0xffffffffu;
+            }
+            const uint4* img4 = reinterpret_cast<const uint4*>(p.img);
+            uint4 pre[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (uoff[i] != 0xffffffffu) pre[i] = __ldg(img4 + uoff[i]);
+            for (int dy = 0; dy < p.patch; ++dy) {
+                __syncwarp();   // every lane has finished converting the previous pixel row out of the strip buffer
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (uoff[i] != 0xffffffffu) *reinterpret_cast<uint4*>(strip + (size_t)(lane + 32 * i) * 16) = pre[i];
+                __syncwarp();
+                if (dy + 1 < p.patch) {   // next pixel row's loads fly while this one is converted
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (uoff[i] != 0xffffffffu) pre[i] = __ldg(img4 + uoff[i] + (size_t)(dy + 1) * upr);
+                }
+                for (int j = 0; j < p.kbpd; ++j) {
+                    const int nvals = min(64, p.seg - 64 * j);   // k values of this k-block (even: seg is even)
+                    const int cj = j % 3;                          // channel of the k-block's first byte: (64 j) % 3
+                    float sc[3], sh[3];
+#pragma unroll
+                    for (int x = 0; x < 3; ++x) {
+                        const int c = (x + cj) % 3;
+                        sc[x] = p.nscale[c];
+                        sh[x] = p.nshift[c];
+                    }
+                    const uint8_t* src = strip + my_off + 64 * j;
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* dst = smem_a + (size_t)stage * A_STAGE_BYTES + (size_t)r * 128;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (u * 8 < ((nvals + 15) & ~15)) {   // whole UMMA_K steps (zero filled); later ones are never issued
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                const int k = u * 8 + e;
+                                const uint32_t two = k < nvals ? *reinterpret_cast<const uint16_t*>(src + k) : 0u;
+                                f[e] = k < nvals ? fmaf((float)(two & 0xffu), sc[k % 3], sh[k % 3]) : 0.f;
+                                f[e + 1] = k < nvals ? fmaf((float)(two >> 8), sc[(k + 1) % 3], sh[(k + 1) % 3]) : 0.f;
+                            }
+                            *reinterpret_cast<uint4*>(dst + ((u ^ (r & 7)) << 4)) =
+                                make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                           pack_bf16x2(f[6], f[7]));
+                        }
+                    }
+                    ptx::fence_proxy_async_smem();   // generic-proxy stores -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive_cluster(leader_full0 + (uint32_t)stage * 8u);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
             }
         }
     }
@@ -454,18 +642,33 @@ void configure() {
     static std::once_flag once;
     std::call_once(once, [] {
         const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 8>, attr, (int)Cfg<256, 8>::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 8>, attr, (int)Cfg<128, 8>::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<64, 8>, attr, (int)Cfg<64, 8>::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 16>, attr, (int)Cfg<256, 16>::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 16>, attr, (int)Cfg<128, 16>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 8, false>, attr, (int)Cfg<256, 8>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 8, false>, attr, (int)Cfg<128, 8>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<64, 8, false>, attr, (int)Cfg<64, 8>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 16, false>, attr, (int)Cfg<256, 16>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 16, false>, attr, (int)Cfg<128, 16>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<256, 8, true>, attr, (int)Cfg<256, 8, true>::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(gemm_kernel<128, 8, true>, attr, (int)Cfg<128, 8, true>::SMEM_BYTES));
     });
 }
 
-template <int BN, int EW>
+template <int BN, int EW, bool GATHER = false>
 static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const Epilogue& ep,
-                      int sms, cudaStream_t stream) {
-    Params p;
+                      int sms, cudaStream_t stream, const PatchGather* pg = nullptr) {
+    Params p{};
+    if (GATHER) {
+        p.img = pg->img;
+        p.patch = pg->patch;
+        p.g = pg->S / pg->patch;
+        p.row_bytes = 3 * pg->S;
+        p.seg = 3 * pg->patch;
+        p.kbpd = patch_gather_kbpd(pg->patch);
+        p.last_steps = (p.seg - 64 * (p.kbpd - 1) + UMMA_K - 1) / UMMA_K;
+        for (int c = 0; c < 3; ++c) {
+            p.nscale[c] = (float)(1.0 / (255.0 * (double)pg->std[c]));
+            p.nshift[c] = (float)(-(double)pg->mean[c] / (double)pg->std[c]);
+        }
+    }
     p.M = M;
     p.N = N;
     p.K = K;
@@ -473,8 +676,11 @@ static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     p.tiles_n = (N + BN - 1) / BN;
     p.super_m = (p.tiles_m + CLUSTER - 1) / CLUSTER;
     p.ep = ep;
-    CUtensorMap ta = make_tmap_2d(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, BK,
-                                  BM, CU_TENSOR_MAP_SWIZZLE_128B);
+    // (GATHER has no A matrix: the A map is a second, unused view of W so the kernel signature stays the same)
+    CUtensorMap ta = GATHER ? make_tmap_2d(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2,
+                                           BK, BN / CLUSTER, CU_TENSOR_MAP_SWIZZLE_128B)
+                            : make_tmap_2d(A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)M,
+                                           (uint64_t)lda * 2, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
     // each CTA of the pair fetches (and keeps) BN / 2 rows of the W tile
     CUtensorMap tb = make_tmap_2d(W, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)K, (uint64_t)N, (uint64_t)K * 2, BK,
                                   BN / CLUSTER, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -482,8 +688,8 @@ static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     const int clusters = std::min(p.super_m * p.tiles_n, max_clusters);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * CLUSTER);
-    cfg.blockDim = dim3(Cfg<BN, EW>::THREADS);
-    cfg.dynamicSmemBytes = Cfg<BN, EW>::SMEM_BYTES;
+    cfg.blockDim = dim3(Cfg<BN, EW, GATHER>::THREADS);
+    cfg.dynamicSmemBytes = Cfg<BN, EW, GATHER>::SMEM_BYTES;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -492,7 +698,31 @@ static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MB_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EW>, ta, tb, p));
+    MB_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EW, GATHER>, ta, tb, p));
+}
+
+bool patch_gather_supported(int S, int patch) {
+    if (S <= 0 || patch <= 0 || S % patch != 0 || patch % 2 != 0) return false;
+    if ((3 * S) % 16 != 0 || 3 * S > GATHER_MAX_ROW_BYTES) return false;
+    const int g = S / patch;
+    return 31 / g + 2 <= GATHER_MAX_ROWS;   // image-row strips under 32 consecutive patches
+}
+
+void launch_patch_embed(const PatchGather& pg, const __nv_bfloat16* Wg, int N, const Epilogue& ep, int sms,
+                        cudaStream_t stream) {
+    if (pg.n <= 0 || N <= 0) return;
+    if (!patch_gather_supported(pg.S, pg.patch))
+        fail(B200_ERR_INTERNAL, "patch gather: image %d / patch %d is not supported", pg.S, pg.patch);
+    if (N % 32 != 0 || ep.ldo % 8 != 0) fail(B200_ERR_INTERNAL, "patch gather: N = %d, ldo = %d", N, ep.ldo);
+    if (ep.residual != nullptr || !ep.out_fp32) fail(B200_ERR_INTERNAL, "patch gather: fp32 output without residual only");
+    configure();
+    const int g = pg.S / pg.patch;
+    const long long M = (long long)pg.n * g * g;
+    if (M > 0x7fffffffLL || (long long)pg.n * pg.S * pg.S * 3 / 16 >= 0xffffffffLL)
+        fail(B200_ERR_INVALID_ARG, "patch gather: batch of %d images is too large", pg.n);
+    const int K = patch_gather_k(pg.patch);
+    if (N % 256 == 0 || N > 512) launch_bn<256, 8, true>(nullptr, 0, Wg, (int)M, N, K, ep, sms, stream, &pg);
+    else launch_bn<128, 8, true>(nullptr, 0, Wg, (int)M, N, K, ep, sms, stream, &pg);
 }
 
 void launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int N, int K, const Epilogue& ep, int sms,
@@ -501,6 +731,11 @@ void launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int 
     if (K <= 0 || K % BK != 0) fail(B200_ERR_INTERNAL, "gemm: K = %d must be a positive multiple of %d", K, BK);
     if (N % 32 != 0) fail(B200_ERR_INTERNAL, "gemm: N = %d must be a multiple of 32", N);
     if (lda % 8 != 0 || ep.ldo % 8 != 0) fail(B200_ERR_INTERNAL, "gemm: leading dimensions must be multiples of 8");
+    if (ep.ln_gamma != nullptr) {
+        if (!ep.out_fp32 || ep.ldo != N || N % 128 != 0 || N > 1024 || ep.remap_group != 0 || !ep.ln_beta ||
+            !ep.ln_counters || (!ep.ln_out_bf16 && !ep.ln_out_f32))
+            fail(B200_ERR_INTERNAL, "gemm: fused LayerNorm needs a compact fp32 output of width N %% 128 == 0, N <= 1024");
+    }
     configure();
     // bf16 output, no residual / token scatter (QKV, fc1): the 16-warp epilogue.  MARQO_B200_GEMM_EPI8=1 keeps the
     // general 8-warp epilogue for A/B timing.

@@ -413,6 +413,27 @@ void pad_rows_to_bf16(const float* src, int rows, int k, int kpad, __nv_bfloat16
     MB_CUDA(cudaGetLastError());
 }
 
+// conv1.weight [w, 3, p, p] -> the gather GEMM's K order: k' = dy * (64 * kbpd) + dx * 3 + c, zero in the padding slots
+__global__ void patch_weight_rows_kernel(const float* __restrict__ src, int rows, int p, int kbpd,
+                                         __nv_bfloat16* __restrict__ dst) {
+    const int kprime = p * kbpd * 64;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rows * kprime) return;
+    const int r = (int)(i / kprime), k = (int)(i - (long long)r * kprime);
+    const int dy = k / (64 * kbpd), q = k - dy * 64 * kbpd;
+    float v = 0.f;
+    if (q < 3 * p) {
+        const int dx = q / 3, c = q - 3 * dx;
+        v = src[(long long)r * 3 * p * p + (long long)c * p * p + dy * p + dx];
+    }
+    dst[i] = __float2bfloat16_rn(v);
+}
+void patch_weight_rows(const float* src, int rows, int p, int kbpd, __nv_bfloat16* dst, cudaStream_t s) {
+    const long long n = (long long)rows * p * kbpd * 64;
+    patch_weight_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, rows, p, kbpd, dst);
+    MB_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------------ resize
 // Pillow's ImagingResample for 8-bit images, restated: per-output-pixel coefficient windows computed in double on
 // the host exactly as precompute_coeffs()/normalize_coeffs_8bpc() do (bicubic a = -0.5, support widened by the

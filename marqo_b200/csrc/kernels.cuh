@@ -46,6 +46,10 @@ void f32_to_bf16(const float* src, __nv_bfloat16* dst, long long n, cudaStream_t
 // conv1.weight [w, 3*p*p] -> bf16 [w, kpad] zero padded
 void pad_rows_to_bf16(const float* src, int rows, int k, int kpad, __nv_bfloat16* dst, cudaStream_t s);
 
+// conv1.weight [w, 3, p, p] (fp32) -> bf16 [w, p * kbpd * 64] in the gather GEMM's K order (gemm.cuh: PatchGather):
+// k' = dy * (64 * kbpd) + dx * 3 + c; the slots past 3 * p of every pixel row are zero.
+void patch_weight_rows(const float* src, int rows, int p, int kbpd, __nv_bfloat16* dst, cudaStream_t s);
+
 // PIL-compatible antialiased bicubic resize (shortest side -> S) + centre crop, uint8 HWC in/out.
 void resize_crop_u8(const uint8_t* src, int n, int h, int w, int S, uint8_t* dst, cudaStream_t s);
 

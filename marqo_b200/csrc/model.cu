@@ -48,6 +48,7 @@ struct TowerW {
     std::vector<LayerW> layers;
     // vision
     const __nv_bfloat16* conv_w = nullptr;  // [width, kpad]
+    const __nv_bfloat16* conv_wg = nullptr; // [width, gemm::patch_gather_k(patch)]: gather GEMM order, or NULL if unsupported
     int kpad = 0, grid = 0, tokens = 0;
     const float *cls = nullptr, *pos = nullptr, *ln_pre_w = nullptr, *ln_pre_b = nullptr;
     // final LN (ln_post / ln_final) and projection [width, embed]
@@ -71,6 +72,7 @@ struct b200_model {
     long long max_tokens = 0;
     float* x = nullptr;
     __nv_bfloat16 *h = nullptr, *qkv = nullptr, *o = nullptr, *u = nullptr, *patches = nullptr;
+    int* ln_counters = nullptr;   // int32 [ceil(max tokens / 32)], zero between launches (gemm.cuh: fused LayerNorm)
     int32_t *aux = nullptr;           // [max_batch] eot index / kv_len
     float* out_dev = nullptr;         // [max_batch, embed]
     float* pooled = nullptr;          // [max_batch, width] LayerNorm-ed pooled rows (CLIP heads)
@@ -126,6 +128,7 @@ void model_free(b200_model* m) {
     cudaFree(m->o);
     cudaFree(m->u);
     cudaFree(m->patches);
+    cudaFree(m->ln_counters);
     cudaFree(m->aux);
     cudaFree(m->out_dev);
     cudaFree(m->pooled);
@@ -272,12 +275,36 @@ void attend(b200_model* m, Counter& c, int B, int S, int w, int heads, int mask_
     c.n += attention::launch(m->qkv, m->o, B, S, w, heads, mask_mode, kv_len, m->stream);
 }
 
-// Pre-LN residual blocks (open_clip ResidualAttentionBlock).
+// LayerNorm fused into the producing residual GEMM's epilogue (gemm.cuh: Epilogue::ln_*); MARQO_B200_NO_LN_FUSION=1
+// keeps the separate LayerNorm launches (A/B timing).
+bool ln_fusion_enabled() {
+    static const bool on = getenv("MARQO_B200_NO_LN_FUSION") == nullptr;
+    return on;
+}
+
+void fuse_ln(b200_model* m, gemm::Epilogue& e, const float* gamma, const float* beta, float eps, float* out_f32,
+             __nv_bfloat16* out_bf16) {
+    e.ln_gamma = gamma;
+    e.ln_beta = beta;
+    e.ln_eps = eps;
+    e.ln_out_f32 = out_f32;
+    e.ln_out_bf16 = out_bf16;
+    e.ln_counters = m->ln_counters;
+}
+
+// Pre-LN residual blocks (open_clip ResidualAttentionBlock).  x (fp32) is the residual stream, h (bf16) the LayerNorm
+// output the next GEMM consumes: ln_1 of layer 0 is a launch of its own, every other LayerNorm runs inside the epilogue
+// of the GEMM that produces its input (out_proj -> ln_2, fc2 -> ln_1 of the next layer).
 void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, int mask_mode) {
     const int M = B * S, w = T.d.width, mlp = T.d.mlp;
     const int act = m->desc.act == B200_ACT_QUICKGELU ? gemm::ACT_QUICKGELU : gemm::ACT_GELU;
-    for (const LayerW& L : T.layers) {
-        kernels::layernorm(m->x, w, L.ln1_w, L.ln1_b, 1e-5f, M, w, nullptr, m->h, m->stream);
+    const bool fused = ln_fusion_enabled();
+    for (size_t li = 0; li < T.layers.size(); ++li) {
+        const LayerW& L = T.layers[li];
+        if (!fused || li == 0) {
+            kernels::layernorm(m->x, w, L.ln1_w, L.ln1_b, 1e-5f, M, w, nullptr, m->h, m->stream);
+            ++c.n;
+        }
         gemm::Epilogue e1;
         e1.bias = L.b_qkv;
         e1.out = m->qkv;
@@ -291,8 +318,12 @@ void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, i
         e2.out = m->x;
         e2.ldo = w;
         e2.out_fp32 = 1;
+        if (fused) fuse_ln(m, e2, L.ln2_w, L.ln2_b, 1e-5f, nullptr, m->h);
         linear(m, c, m->o, M, w, L.w_o, w, e2);
-        kernels::layernorm(m->x, w, L.ln2_w, L.ln2_b, 1e-5f, M, w, nullptr, m->h, m->stream);
+        if (!fused) {
+            kernels::layernorm(m->x, w, L.ln2_w, L.ln2_b, 1e-5f, M, w, nullptr, m->h, m->stream);
+            ++c.n;
+        }
         gemm::Epilogue e3;
         e3.bias = L.b_fc;
         e3.act = act;
@@ -306,15 +337,18 @@ void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, i
         e4.out = m->x;
         e4.ldo = w;
         e4.out_fp32 = 1;
+        if (fused && li + 1 < T.layers.size())
+            fuse_ln(m, e4, T.layers[li + 1].ln1_w, T.layers[li + 1].ln1_b, 1e-5f, nullptr, m->h);
         linear(m, c, m->u, M, mlp, L.w_proj, w, e4);
-        c.n += 2;   // the two LayerNorm launches
     }
 }
 
-// Post-LN blocks (HF BertLayer); on entry x (fp32) and h (bf16) both hold the embedding LayerNorm output.
+// Post-LN blocks (HF BertLayer); on entry x (fp32) and h (bf16) both hold the embedding LayerNorm output.  Both
+// LayerNorms of a layer run inside the epilogue of the GEMM before them and rewrite x in place.
 void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
     const int M = B * S, w = T.d.width, mlp = T.d.mlp;
     const float eps = 1e-12f;
+    const bool fused = ln_fusion_enabled();
     for (const LayerW& L : T.layers) {
         gemm::Epilogue e1;
         e1.bias = L.b_qkv;
@@ -329,8 +363,12 @@ void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
         e2.out = m->x;
         e2.ldo = w;
         e2.out_fp32 = 1;
+        if (fused) fuse_ln(m, e2, L.ln1_w, L.ln1_b, eps, m->x, m->h);
         linear(m, c, m->o, M, w, L.w_o, w, e2);
-        kernels::layernorm(m->x, w, L.ln1_w, L.ln1_b, eps, M, w, m->x, m->h, m->stream);
+        if (!fused) {
+            kernels::layernorm(m->x, w, L.ln1_w, L.ln1_b, eps, M, w, m->x, m->h, m->stream);
+            ++c.n;
+        }
         gemm::Epilogue e3;
         e3.bias = L.b_fc;
         e3.act = gemm::ACT_GELU;
@@ -344,9 +382,12 @@ void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
         e4.out = m->x;
         e4.ldo = w;
         e4.out_fp32 = 1;
+        if (fused) fuse_ln(m, e4, L.ln2_w, L.ln2_b, eps, m->x, m->h);
         linear(m, c, m->u, M, mlp, L.w_proj, w, e4);
-        kernels::layernorm(m->x, w, L.ln2_w, L.ln2_b, eps, M, w, m->x, m->h, m->stream);
-        c.n += 2;   // the two LayerNorm launches
+        if (!fused) {
+            kernels::layernorm(m->x, w, L.ln2_w, L.ln2_b, eps, M, w, m->x, m->h, m->stream);
+            ++c.n;
+        }
     }
 }
 
@@ -355,20 +396,40 @@ void forward_images_eager(b200_model* m, Counter& c, const uint8_t* u8, const fl
                           float* d_out) {
     const TowerW& T = m->vision;
     const int S = T.d.image_size, p = T.d.patch, w = T.d.width, G = T.grid * T.grid;
-    if (u8)
-        kernels::im2col_u8(u8, n, S, p, T.kpad, m->desc.image_mean, m->desc.image_std, m->patches, m->stream);
-    else
-        kernels::im2col_f32(f32, n, S, p, T.kpad, m->patches, m->stream);
     gemm::Epilogue e;  // conv1 (no bias) + positional embedding, scattered to token rows 1..G of each image
     e.out = m->x;
     e.ldo = w;
     e.out_fp32 = 1;
     e.remap_group = G;
     e.rowbias = T.pos;
-    linear(m, c, m->patches, n * G, T.kpad, T.conv_w, w, e);
+    static const bool no_gather = getenv("MARQO_B200_NO_PATCH_GATHER") != nullptr;   // A/B timing switch
+    if (u8 && T.conv_wg && !no_gather && (reinterpret_cast<uintptr_t>(u8) & 15) == 0) {
+        // uint8 pixels -> ToTensor + Normalize -> bf16 inside the GEMM's operand load: no patch matrix in HBM
+        gemm::PatchGather pg;
+        pg.img = u8;
+        pg.n = n;
+        pg.S = S;
+        pg.patch = p;
+        for (int i = 0; i < 3; ++i) {
+            pg.mean[i] = m->desc.image_mean[i];
+            pg.std[i] = m->desc.image_std[i];
+        }
+        ProfScope ps(m, 0);
+        gemm::launch_patch_embed(pg, T.conv_wg, w, e, m->sms, m->stream);
+        ++c.n;
+    } else {
+        // preprocessed fp32 CHW tensors (the reference's parity path) and shapes the gather does not cover
+        if (!m->patches) dev_alloc((void**)&m->patches, (size_t)m->desc.max_batch * G * T.kpad * 2);
+        if (u8)
+            kernels::im2col_u8(u8, n, S, p, T.kpad, m->desc.image_mean, m->desc.image_std, m->patches, m->stream);
+        else
+            kernels::im2col_f32(f32, n, S, p, T.kpad, m->patches, m->stream);
+        linear(m, c, m->patches, n * G, T.kpad, T.conv_w, w, e);
+        ++c.n;
+    }
     kernels::vit_cls_rows(m->x, T.cls, T.pos, n, T.tokens, w, m->stream);
     kernels::layernorm(m->x, w, T.ln_pre_w, T.ln_pre_b, 1e-5f, n * T.tokens, w, m->x, nullptr, m->stream);
-    c.n += 3;
+    c.n += 2;
     run_clip_blocks(m, c, T, n, T.tokens, attention::MASK_NONE);
     kernels::clip_head(m->x, T.tokens, nullptr, T.ln_out_w, T.ln_out_b, 1e-5f, T.proj, n, w, m->desc.embed_dim, normalize,
                        d_out, m->pooled, m->stream);
@@ -623,6 +684,14 @@ int b200_model_finalize(b200_model* m) {
             kernels::pad_rows_to_bf16(conv, (int)w, K, T.kpad, cw, m->stream);
             MB_CUDA(cudaStreamSynchronize(m->stream));
             T.conv_w = cw;
+            if (gemm::patch_gather_supported(T.d.image_size, (int)p)) {
+                __nv_bfloat16* cg = nullptr;
+                dev_alloc((void**)&cg, (size_t)w * gemm::patch_gather_k((int)p) * 2);
+                m->owned.push_back(cg);
+                kernels::patch_weight_rows(conv, (int)w, (int)p, gemm::patch_gather_kbpd((int)p), cg, m->stream);
+                MB_CUDA(cudaStreamSynchronize(m->stream));
+                T.conv_wg = cg;
+            }
             T.cls = param(m, "visual.class_embedding", w);
             T.pos = param(m, "visual.positional_embedding", (long long)T.tokens * w);
             T.ln_pre_w = param(m, "visual.ln_pre.weight", w);
@@ -634,7 +703,9 @@ int b200_model_finalize(b200_model* m) {
             max_tok = std::max(max_tok, (long long)m->desc.max_batch * T.tokens);
             max_w = std::max(max_w, w);
             max_mlp = std::max(max_mlp, (long long)T.d.mlp);
-            dev_alloc((void**)&m->patches, (size_t)m->desc.max_batch * T.grid * T.grid * T.kpad * 2);
+            // the bf16 patch matrix of the im2col path is allocated on first use (fp32 CHW input / unsupported shapes)
+            if (!T.conv_wg)
+                dev_alloc((void**)&m->patches, (size_t)m->desc.max_batch * T.grid * T.grid * T.kpad * 2);
             dev_alloc((void**)&m->resized, (size_t)m->desc.max_batch * T.d.image_size * T.d.image_size * 3);
         }
         if (m->text.present) {
@@ -670,6 +741,9 @@ int b200_model_finalize(b200_model* m) {
         dev_alloc((void**)&m->qkv, (size_t)m->max_tokens * max_w * 6);
         dev_alloc((void**)&m->o, (size_t)m->max_tokens * max_w * 2);
         dev_alloc((void**)&m->u, (size_t)m->max_tokens * max_mlp * 2);
+        dev_alloc((void**)&m->ln_counters, (size_t)(m->max_tokens / 32 + 2) * 4);
+        MB_CUDA(cudaMemsetAsync(m->ln_counters, 0, (size_t)(m->max_tokens / 32 + 2) * 4, m->stream));
+        MB_CUDA(cudaStreamSynchronize(m->stream));
         dev_alloc((void**)&m->aux, (size_t)m->desc.max_batch * 4);
         dev_alloc((void**)&m->out_dev, (size_t)m->desc.max_batch * E * 4);
         dev_alloc((void**)&m->pooled, (size_t)m->desc.max_batch * max_w * 4);

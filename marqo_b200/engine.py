@@ -489,6 +489,38 @@ def debug_gemm(A, W, bias=None, residual=None, act: int = 0, out_bf16: bool = Fa
     return out
 
 
+def debug_gemm_ln(A, W, bias, residual, gamma, beta, eps: float, in_place: bool = False, repeats: int = 1,
+                  device: int = 0):
+    """Residual GEMM with fused LayerNorm -> (x fp32 [M, N], LayerNorm(x) rounded to bf16 [M, N])."""
+    A, W = _as(A, np.float32), _as(W, np.float32)
+    M, K = A.shape
+    Nn = W.shape[0]
+    b = None if bias is None else _as(bias, np.float32)
+    r = None if residual is None else _as(residual, np.float32)
+    g, be = _as(gamma, np.float32), _as(beta, np.float32)
+    out_x = np.empty((M, Nn), np.float32)
+    out_ln = np.empty((M, Nn), np.float32)
+    N.check(N.load().b200_debug_gemm_ln(device, _ptr(A), _ptr(W), _ptr(b), _ptr(r), M, Nn, K, _ptr(g), _ptr(be),
+                                        float(eps), 1 if in_place else 0, repeats, _ptr(out_x), _ptr(out_ln)))
+    return out_x, out_ln
+
+
+def debug_patch_embed(images_u8, patch: int, conv_w, mean, std, pos=None, use_gather: bool = True,
+                      device: int = 0) -> np.ndarray:
+    """ViT patch embedding of uint8 HWC images [n, S, S, 3] -> token rows fp32 [n * (G + 1), N] (class rows zero)."""
+    img = _as(images_u8, np.uint8)
+    n, S = img.shape[0], img.shape[1]
+    w = _as(conv_w, np.float32).reshape(conv_w.shape[0], -1)
+    Nn = w.shape[0]
+    G = (S // patch) ** 2
+    m3, s3 = _as(mean, np.float32), _as(std, np.float32)
+    ps = None if pos is None else _as(pos, np.float32)
+    out = np.empty((n * (G + 1), Nn), np.float32)
+    N.check(N.load().b200_debug_patch_embed(device, _ptr(img), n, S, patch, _ptr(w), Nn, _ptr(m3), _ptr(s3), _ptr(ps),
+                                            1 if use_gather else 0, _ptr(out)))
+    return out
+
+
 def debug_attention(qkv, B: int, S: int, W: int, H: int, mask: int = 0, kv_len=None, device: int = 0) -> np.ndarray:
     q = _as(qkv, np.float32)
     kl = None if kv_len is None else _as(kv_len, np.int32)
