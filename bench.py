@@ -74,11 +74,28 @@ def emit(line: dict):
 
 
 def host_threads() -> int:
-    """Threads this process may actually use (cgroup / affinity aware), not the box's core count."""
+    """Threads this process may actually use: the affinity mask capped by the cgroup CPU quota (a 128-CPU mask
+    under an 8-CPU quota runs torch 16x oversubscribed and several times slower), not the box's core count."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, -(-int(parts[0]) // int(parts[1]))))
+            else:
+                quota = int(parts[0])
+                if quota > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as f:
+                        n = min(n, max(1, -(-quota // int(f.read().split()[0]))))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
 
 
 def load_peaks():

@@ -383,9 +383,8 @@ int b200_debug_gemm(int device, const float* A, const float* W, const float* bia
                     int K, int act, int out_bf16, float* out);
 /* Residual GEMM with the LayerNorm fused into its epilogue (gemm.cuh Epilogue::ln_*): out_x fp32 [M,N] = A W^T + bias
  * (+ residual); out_ln = LayerNorm(out_x) * gamma + beta rounded to bf16 (returned as fp32).  in_place != 0: the fp32
- * normalised rows also replace out_x (BERT post-LN).  The launch is repeated `repeats` times on the same strip counters
- * (they must return to zero); with a residual and in_place == 0 the residual input is never modified, so every
- * repeat computes the same thing. */
+ * normalised rows also replace out_x (BERT post-LN).  The launch is repeated `repeats` times, alternating between two strip
+ * counter arrays as the model's out_proj / fc2 do; with in_place == 0 every repeat computes the same thing. */
 int b200_debug_gemm_ln(int device, const float* A, const float* W, const float* bias, const float* residual, int M, int N,
                        int K, const float* gamma, const float* beta, float eps, int in_place, int repeats, float* out_x,
                        float* out_ln);

@@ -2,8 +2,9 @@
 //
 // All keys of a sequence fit ONE tcgen05.mma of N = 256, so there is no online softmax: per (batch, head, 128 queries)
 //   S = Q K^T        (M = 128, N = 256, K = 64)   -> TMEM columns [0, 256)   one instruction group, one hand-off
-//   exact row maximum (pass 1 over S in TMEM), P = exp2(S * scale - max) (pass 2) written back INTO TMEM as packed bf16
-//   pairs over the columns of S that pass 2 has already consumed ([0, 128)),
+//   P = exp2(S * scale - ref) in ONE pass over S in TMEM (ref = the row's first-chunk maximum + 32: any reference gives the
+//   same softmax, see the softmax warps), written back INTO TMEM as packed bf16 pairs over the columns of S the pass has
+//   already consumed ([0, 128)),
 //   O = P V          (M = 128, N = 64, K = 256; A operand read from TMEM, V MN-major from smem) -> columns [128, 192)
 //   epilogue: O / l (+ the remainder key of 257 = 256 + 1) -> bf16.
 // Compared with attention_tc.cu (128-key blocks, P through shared memory, running maximum + O rescale) an item has one
@@ -35,13 +36,14 @@ constexpr int NK = 256;                       // keys covered by the one S tile
 constexpr int THREADS = 224;
 constexpr uint32_t Q_BYTES = BQ * HD * 2;     // 16 KB
 constexpr uint32_t KV_BYTES = NK * HD * 2;    // 32 KB each for K and V
-constexpr uint32_t TAILS_BYTES = BQ * 4;
-constexpr uint32_t TAILV_BYTES = HD * 2;
+constexpr int TAIL_ROWS = 16;                 // the remainder key travels as a 16-row TMA box (rows 1..15: next sequence / zero fill)
+constexpr uint32_t TAIL_BYTES = TAIL_ROWS * HD * 2;   // 2 KB each for the remainder key's K tile and V tile
 constexpr uint32_t BAR_BYTES = 256;
-constexpr uint32_t SMEM_BYTES = 2 * Q_BYTES + 2 * KV_BYTES + BAR_BYTES + TAILS_BYTES + TAILV_BYTES;
+constexpr uint32_t SMEM_BYTES = 2 * Q_BYTES + 2 * KV_BYTES + 2 * TAIL_BYTES + BAR_BYTES;
 static_assert(SMEM_BYTES <= 115712, "two CTAs per SM");
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t S_COL = 0, P_COL = 0, O_COL = 128;
+constexpr uint32_t T_COL = 192;   // remainder key's scores (N = 16 MMA, column 0 is the key), written after S is consumed
 
 __device__ __forceinline__ float ex2(float x) {
     float y;
@@ -75,6 +77,9 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&v)[32]) {
                    "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
                  :
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x1(uint32_t taddr, uint32_t& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
 // 32 lanes x 16 columns: registers -> TMEM (thread t writes lane base_lane + t)
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -130,14 +135,17 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], int c, int kh
 
 template <int MASK>
 __global__ void __launch_bounds__(THREADS, 2)
-attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat16* __restrict__ qkv,
+attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
+                    const __nv_bfloat16* __restrict__ qkv,
                     __nv_bfloat16* __restrict__ out, int S, int W, int H, const int32_t* __restrict__ kv_len,
                     float scale_log2e, int s_main, int has_tail, int total_units) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;                         // two 16 KB tiles
     uint8_t* sK = sQ + 2 * Q_BYTES;             // 256 keys x 64 dims, K-major 128B-swizzled (two TMA boxes)
     uint8_t* sV = sK + KV_BYTES;                // 256 keys x 64 dims: the MN-major B operand of P V
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_BYTES);
+    uint8_t* sKt = sV + KV_BYTES;               // remainder key: K rows s_main .. s_main + 15 (row 0 is the key)
+    uint8_t* sVt = sKt + TAIL_BYTES;            // ... and its V rows (row 0 = 128 contiguous bytes: swizzle is the identity there)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sVt + TAIL_BYTES);
     uint64_t* q_full = bars;          // [2]
     uint64_t* q_empty = bars + 2;     // [2]
     uint64_t* k_full = bars + 4;
@@ -148,11 +156,8 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
     uint64_t* p_full = bars + 9;
     uint64_t* o_full = bars + 10;
     uint64_t* tmem_free = bars + 11;
-    uint64_t* tail_full = bars + 12;
-    uint64_t* tail_empty = bars + 13;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-    float* sTailS = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + BAR_BYTES);
-    __nv_bfloat16* sTailV = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(sTailS) + TAILS_BYTES);
+    const __nv_bfloat16* sTailV = reinterpret_cast<const __nv_bfloat16*>(sVt);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -161,20 +166,19 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmap);
+        ptx::prefetch_tmap(&tmap_tail);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&q_full[i], 1);
-            ptx::mbar_init(&q_empty[i], 2);   // the S MMA's commit + warp 6 (remainder-key scores read the Q tile)
+            ptx::mbar_init(&q_empty[i], 1);   // the commit after the item's last MMA that reads the Q tile
         }
         ptx::mbar_init(k_full, 1);
         ptx::mbar_init(k_empty, 2);           // the last S MMA's commit + warp 6 (remainder row)
         ptx::mbar_init(v_full, 1);
-        ptx::mbar_init(v_empty, 2);           // the last P V's commit + warp 6
+        ptx::mbar_init(v_empty, has_tail ? 6 : 2);   // the last P V's commit + warp 6 (+ the 4 epilogue warps: remainder V row)
         ptx::mbar_init(s_full, 1);
         ptx::mbar_init(p_full, 4);
         ptx::mbar_init(o_full, 1);
         ptx::mbar_init(tmem_free, 4);
-        ptx::mbar_init(tail_full, 1);
-        ptx::mbar_init(tail_empty, 4);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -202,15 +206,19 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                     ptx::tma_load_2d(sQ + buf * Q_BYTES, &tmap, &q_full[buf], h * HD, row_base + qb * BQ, ptx::kEvictNormal);
                     if (qb == 0) {
                         ptx::mbar_wait(k_empty, (uc & 1) ^ 1);
-                        ptx::mbar_arrive_expect_tx(k_full, KV_BYTES);
+                        ptx::mbar_arrive_expect_tx(k_full, KV_BYTES + (has_tail ? TAIL_BYTES : 0));
                         ptx::tma_load_2d(sK, &tmap, k_full, W + h * HD, row_base, ptx::kEvictNormal);
                         ptx::tma_load_2d(sK + KV_BYTES / 2, &tmap, k_full, W + h * HD, row_base + 128, ptx::kEvictNormal);
+                        if (has_tail)
+                            ptx::tma_load_2d(sKt, &tmap_tail, k_full, W + h * HD, row_base + s_main, ptx::kEvictNormal);
                     } else {
                         ptx::mbar_wait(v_empty, (uc & 1) ^ 1);
-                        ptx::mbar_arrive_expect_tx(v_full, KV_BYTES);
+                        ptx::mbar_arrive_expect_tx(v_full, KV_BYTES + (has_tail ? TAIL_BYTES : 0));
                         ptx::tma_load_2d(sV, &tmap, v_full, 2 * W + h * HD, row_base, ptx::kEvictNormal);
                         ptx::tma_load_2d(sV + KV_BYTES / 2, &tmap, v_full, 2 * W + h * HD, row_base + 128,
                                          ptx::kEvictNormal);
+                        if (has_tail)
+                            ptx::tma_load_2d(sVt, &tmap_tail, v_full, 2 * W + h * HD, row_base + s_main, ptx::kEvictNormal);
                     }
                 }
             }
@@ -219,6 +227,7 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         // ================================================================== MMA issuer
         constexpr uint32_t idesc_s = ptx::make_idesc_f16_major(1, BQ, NK, 0, 0);
         constexpr uint32_t idesc_o = ptx::make_idesc_f16_major(1, BQ, HD, 0, 1);   // A (P) K-major in TMEM, B (V) MN-major
+        constexpr uint32_t idesc_t = ptx::make_idesc_f16_major(1, BQ, TAIL_ROWS, 0, 0);   // Q x (remainder key tile)^T
         uint32_t n = 0, uc = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++uc) {
             for (int qb = 0; qb < q_blocks; ++qb, ++n) {
@@ -235,8 +244,10 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                         ptx::umma_f16(tmem_base + S_COL, ptx::make_desc_k_sw128(q_base + k * 32),
                                       ptx::make_desc_k_sw128(k_base + k * 32), idesc_s, k != 0 ? 1u : 0u);
                     ptx::umma_commit(s_full);
-                    ptx::umma_commit(&q_empty[buf]);
-                    if (qb == q_blocks - 1) ptx::umma_commit(k_empty);
+                    if (!has_tail) {
+                        ptx::umma_commit(&q_empty[buf]);
+                        if (qb == q_blocks - 1) ptx::umma_commit(k_empty);
+                    }
                 }
                 __syncwarp();
                 ptx::mbar_wait(p_full, n & 1);       // P of this item is in TMEM (and S fully consumed)
@@ -248,6 +259,18 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                     for (int k = 0; k < NK / 16; ++k)
                         umma_f16_ts(tmem_base + O_COL, tmem_base + P_COL + k * 8,
                                     ptx::make_desc_mn_sw128(v_base + k * 16 * 128, 8192, 1024), idesc_o, k != 0 ? 1u : 0u);
+                    if (has_tail) {
+                        // the remainder key's scores for the item's 128 rows: a 16-column MMA into columns that S no longer
+                        // needs (all of S has been consumed once P is complete); the epilogue reads column T_COL
+                        const uint32_t q_base = ptx::smem_u32(sQ + buf * Q_BYTES);
+                        const uint32_t kt_base = ptx::smem_u32(sKt);
+#pragma unroll
+                        for (int k = 0; k < HD / 16; ++k)
+                            ptx::umma_f16(tmem_base + T_COL, ptx::make_desc_k_sw128(q_base + k * 32),
+                                          ptx::make_desc_k_sw128(kt_base + k * 32), idesc_t, k != 0 ? 1u : 0u);
+                        ptx::umma_commit(&q_empty[buf]);
+                        if (qb == q_blocks - 1) ptx::umma_commit(k_empty);
+                    }
                     ptx::umma_commit(o_full);
                     if (qb == q_blocks - 1) ptx::umma_commit(v_empty);
                 }
@@ -256,7 +279,7 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         }
     } else if (warp == 6) {
         // ================================================================== remainder key + remainder query row
-        uint32_t n = 0, uc = 0, nt_staged = 0;
+        uint32_t uc = 0;
         const size_t ld = (size_t)3 * W;
         const int gq = lane >> 2, tq = lane & 3;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++uc) {
@@ -264,58 +287,19 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
             const int row_base = b * S;
             int len = S;
             if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[b], 0));
-            const int kend = min(len, s_main);
-            for (int qb = 0; qb < q_blocks; ++qb, ++n) {
-                const uint32_t buf = n & 1;
-                const uint8_t* sQb = sQ + buf * Q_BYTES;
-                ptx::mbar_wait(&q_full[buf], (n >> 1) & 1);
-                if (has_tail && s_main < len) {
-                    const __nv_bfloat16* krow = qkv + ((size_t)row_base + s_main) * ld + W + h * HD;
-                    uint4 k4[HD / 8];
-#pragma unroll
-                    for (int x = 0; x < HD / 8; ++x) k4[x] = __ldg(reinterpret_cast<const uint4*>(krow) + x);
-                    const __nv_bfloat162 v2 = reinterpret_cast<const __nv_bfloat162*>(krow + W)[lane];
-                    if (qb == q_blocks - 1) {
-                        const int nu = u + gridDim.x;
-                        if (lane == 0 && nu < total_units) {   // the next unit's remainder rows: into L2 ahead of time
-                            const int nb = nu / H, nh = nu - nb * H;
-                            const __nv_bfloat16* nrow = qkv + ((size_t)nb * S + s_main) * ld + W + nh * HD;
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + W));
-                            asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow - W));
-                        }
-                    }
-                    if (nt_staged > 0) ptx::mbar_wait(tail_empty, (nt_staged - 1) & 1);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = lane + 32 * i;
-                        float acc = 0.f;
-#pragma unroll
-                        for (int x = 0; x < HD / 8; ++x) {
-                            const uint4 q4 = *reinterpret_cast<const uint4*>(sQb + (size_t)r * 128 + ((x ^ (r & 7)) << 4));
-                            const uint32_t qq[4] = {q4.x, q4.y, q4.z, q4.w};
-                            const uint32_t kk[4] = {k4[x].x, k4[x].y, k4[x].z, k4[x].w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 qa = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&qq[e]));
-                                const float2 ka = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&kk[e]));
-                                acc = fmaf(qa.x, ka.x, acc);
-                                acc = fmaf(qa.y, ka.y, acc);
-                            }
-                        }
-                        sTailS[r] = acc * scale_log2e;
-                    }
-                    reinterpret_cast<__nv_bfloat162*>(sTailV)[lane] = v2;
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(tail_full);
-                    ++nt_staged;
+            {
+                // (the remainder KEY is the tensor core's job: a 16-row K tile + a 16-column MMA per item, see the MMA warp)
+                const int nu = u + gridDim.x;
+                if (has_tail && lane == 0 && nu < total_units) {   // the next unit's remainder row: into L2 ahead of time
+                    const int nb = nu / H, nh = nu - nb * H;
+                    const __nv_bfloat16* nrow = qkv + ((size_t)nb * S + s_main) * ld + nh * HD;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + W));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + 2 * W));
                 }
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&q_empty[buf]);
-                if (qb == 0) {
-                    ptx::mbar_wait(k_full, uc & 1);   // this warp reads K / V in the unit's last item; observe the loads
-                    continue;
-                }
+                // K / V work of this warp happens as soon as the unit's tiles have landed: the sooner this warp hands
+                // K / V back, the sooner the producer can start the next unit's loads (they are single buffered)
+                ptx::mbar_wait(k_full, uc & 1);
                 ptx::mbar_wait(v_full, uc & 1);
                 // ---- remainder row (query index s_main) against the 256 keys in shared memory, row 0 of 16-row mma tiles
                 if (has_tail && s_main < S) {
@@ -453,7 +437,6 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                         ptx::mbar_arrive(v_empty);
                     }
                 }
-                (void)kend;
             }
         }
     } else {
@@ -461,7 +444,7 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
         const int sp = warp & 3;
         const int r = sp * 32 + lane;
         const uint32_t lane_addr = tmem_base + (uint32_t(sp * 32) << 16);
-        uint32_t n = 0, nt = 0;
+        uint32_t n = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const int b = u / H, h = u - b * H;
             const int row_base = b * S;
@@ -476,30 +459,30 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                 ptx::mbar_wait(s_full, n & 1);
                 ptx::tc_fence_after();
                 uint32_t va[32], vb[32];
-                // ---- pass 1: exact row maximum (the next chunk's tcgen05.ld is in flight while this one is reduced)
-                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                // ---- ONE pass over S.  softmax(s) = exp2(s' - ref) / sum exp2(s' - ref) for ANY reference, so the
+                // exponent reference does not have to be the row maximum — only close enough that nothing overflows:
+                // ref = (maximum of the row's first 32 scores) + 32.  A later score may exceed that maximum by up to
+                // 2^159 before exp2 overflows, scores more than 2^94 below it flush to zero next to a term >= 2^-32, and
+                // P, l and O are floating point (bf16 / fp32: 8 exponent bits), so the common factor 2^-32 costs no
+                // precision; it cancels in O / l.  (attention_tc.cu needs the running maximum because it accumulates
+                // over key blocks; here all 256 keys are in TMEM at once.)
                 ptx::tmem_ld_32x32b_x32(lane_addr + S_COL, va);
-#pragma unroll 1
-                for (int c = 0; c < NK / 32; c += 2) {
-                    tmem_ld_wait_regs(va);
-                    ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (c + 1) * 32, vb);
-                    if (full) max_chunk<true>(va, c, khi, mx4);
-                    else max_chunk<false>(va, c, khi, mx4);
-                    tmem_ld_wait_regs(vb);
-                    // (the last prefetch wraps to chunk 0: pass 2 starts with it)
-                    ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + ((c + 2) & (NK / 32 - 1)) * 32, va);
-                    if (full) max_chunk<true>(vb, c + 1, khi, mx4);
-                    else max_chunk<false>(vb, c + 1, khi, mx4);
-                }
-                const float m_run0 = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * scale_log2e;
+                tmem_ld_wait_regs(va);
+                ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + 32, vb);
+                float c0[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                if (full) max_chunk<true>(va, 0, khi, c0);
+                else max_chunk<false>(va, 0, khi, c0);
+                const float cmax = fmaxf(fmaxf(c0[0], c0[1]), fmaxf(c0[2], c0[3]));
+                const float m_run0 = cmax == -INFINITY ? -INFINITY : fmaf(cmax, scale_log2e, 32.0f);
                 const float m_safe = m_run0 == -INFINITY ? 0.f : m_run0;
-                // ---- pass 2: P = exp2(s * scale - max) -> bf16 pairs over the consumed columns of S
                 float ls4[4] = {0.f, 0.f, 0.f, 0.f};
                 const uint32_t p_addr = lane_addr + P_COL;
 #pragma unroll 1
                 for (int c = 0; c < NK / 32; c += 2) {
-                    tmem_ld_wait_regs(va);
-                    ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (c + 1) * 32, vb);
+                    if (c > 0) {
+                        tmem_ld_wait_regs(va);
+                        ptx::tmem_ld_32x32b_x32(lane_addr + S_COL + (c + 1) * 32, vb);
+                    }
                     if (full) exp_chunk<true>(va, c, khi, scale_log2e, m_safe, ls4, p_addr);
                     else exp_chunk<false>(va, c, khi, scale_log2e, m_safe, ls4, p_addr);
                     tmem_ld_wait_regs(vb);
@@ -513,28 +496,29 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(p_full);
-                // ---- remainder key: online update of (m, l); folded into the output below
-                float t_alpha = 1.f, t_p = 0.f;
-                if (has_tail_key) {
-                    ptx::mbar_wait(tail_full, nt & 1);
-                    const float sc = sTailS[r];
-                    const float m_new = fmaxf(m_run, sc);
-                    t_alpha = ex2(m_run - m_new);
-                    const float pe = ex2(sc - m_new);
-                    t_p = __bfloat162float(__float2bfloat16_rn(pe));
-                    l_run = l_run * t_alpha + pe;
-                    m_run = m_new;
-                }
-                const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
                 ptx::mbar_wait(o_full, n & 1);
                 ptx::tc_fence_after();
                 ptx::tmem_ld_32x32b_x32(lane_addr + O_COL, va);
                 ptx::tmem_ld_32x32b_x32(lane_addr + O_COL + 32, vb);
+                uint32_t tsc = 0;
+                if (has_tail) tmem_ld_32x32b_x1(lane_addr + T_COL, tsc);   // q_row . remainder key (fp32 accumulator)
                 ptx::tmem_ld_wait();
                 // O is in registers: the next item's S may overwrite the accumulator columns
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(tmem_free);
+                // ---- remainder key: online update of (m, l); folded into the output below
+                float t_alpha = 1.f, t_p = 0.f;
+                if (has_tail_key) {
+                    const float sc = __uint_as_float(tsc) * scale_log2e;
+                    const float m_new = fmaxf(m_run, sc);
+                    t_alpha = ex2(m_run - m_new);
+                    const float pe = ex2(sc - m_new);
+                    t_p = __bfloat162float(__float2bfloat16_rn(pe));   // the tensor-core path rounds P to bf16 too
+                    l_run = l_run * t_alpha + pe;
+                    m_run = m_new;
+                }
+                const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
                 if (row_valid) {
                     uint4* d4 = reinterpret_cast<uint4*>(out + ((size_t)row_base + qrow) * W + h * HD);
 #pragma unroll
@@ -565,10 +549,10 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __nv_bfloat1
                                                         pack2(o[8 * x + 6] * inv, o[8 * x + 7] * inv));
                     }
                 }
-                if (has_tail_key) {
+                if (has_tail && qb == q_blocks - 1) {
+                    // the remainder key's V row (sVt) has been read for the unit's last item: the V buffers may be refilled
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(tail_empty);
-                    ++nt;
+                    if (lane == 0) ptx::mbar_arrive(v_empty);
                 }
             }
         }
@@ -604,6 +588,9 @@ int launch_os(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     });
     CUtensorMap tmap = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,
                                     (uint64_t)3 * W * 2, os::HD, os::BQ, CU_TENSOR_MAP_SWIZZLE_128B);
+    // the remainder key (row 256 of a 257-token sequence) of K and of V: 16-row boxes of the same matrix
+    CUtensorMap tmap_tail = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,
+                                         (uint64_t)3 * W * 2, os::HD, os::TAIL_ROWS, CU_TENSOR_MAP_SWIZZLE_128B);
     const float scale_log2e = 0.125f * 1.4426950408889634f;
     int device = 0;
     MB_CUDA(cudaGetDevice(&device));
@@ -613,10 +600,10 @@ int launch_os(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     const int grid = std::min(2 * sm_count(device), total_units);
     if (mask == MASK_NONE)
         os::attention_os_kernel<MASK_NONE><<<grid, os::THREADS, os::SMEM_BYTES, stream>>>(
-            tmap, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
+            tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
     else
         os::attention_os_kernel<MASK_KEYLEN><<<grid, os::THREADS, os::SMEM_BYTES, stream>>>(
-            tmap, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
+            tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
     MB_CUDA(cudaGetLastError());
     return 1;
 }

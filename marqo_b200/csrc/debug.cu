@@ -131,8 +131,10 @@ int b200_debug_gemm_ln(int device, const float* A, const float* W, const float* 
         float* dOut = sc.alloc<float>((size_t)M * N);
         __nv_bfloat16* dLnB = sc.alloc<__nv_bfloat16>((size_t)M * N);
         float* dLnF = sc.alloc<float>((size_t)M * N);
-        int* dCnt = sc.alloc<int>((size_t)M / 32 + 2);
-        MB_CUDA(cudaMemsetAsync(dCnt, 0, ((size_t)M / 32 + 2) * 4, sc.s));
+        const size_t strips = (size_t)M / 32 + 2;
+        int* dCnt = sc.alloc<int>(2 * strips);   // two arrays: each launch counts in one and zeroes the other
+        MB_CUDA(cudaMemsetAsync(dCnt, 0, 2 * strips * 4, sc.s));
+        float2* dStats = sc.alloc<float2>((size_t)M * gemm::LN_MAX_PARTS);
         gemm::Epilogue ep;
         ep.bias = bias ? sc.upload(bias, (size_t)N) : nullptr;
         ep.residual = residual ? sc.upload(residual, (size_t)M * N) : nullptr;
@@ -145,9 +147,13 @@ int b200_debug_gemm_ln(int device, const float* A, const float* W, const float* 
         ep.ln_eps = eps;
         ep.ln_out_bf16 = dLnB;
         ep.ln_out_f32 = in_place ? dOut : nullptr;   // BERT post-LN: the normalised rows replace the fp32 output
-        ep.ln_counters = dCnt;
-        // repeated launches on the same counters: they must come back to zero every time
-        for (int i = 0; i < repeats; ++i) gemm::launch(dA, K, dW, M, N, K, ep, sm_count(device), sc.s);
+        ep.ln_stats = dStats;
+        // repeated launches alternate between the two counter arrays, as out_proj / fc2 do in the model
+        for (int i = 0; i < repeats; ++i) {
+            ep.ln_counters = dCnt + (i & 1) * strips;
+            ep.ln_zero = dCnt + ((i + 1) & 1) * strips;
+            gemm::launch(dA, K, dW, M, N, K, ep, sm_count(device), sc.s);
+        }
         const long long n = (long long)M * N;
         bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sc.s>>>(dLnB, dLnF, n);
         MB_CUDA(cudaGetLastError());

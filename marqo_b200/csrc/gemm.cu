@@ -100,10 +100,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(hx, e, hx);
 }
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-    if (act == ACT_GELU) return gelu_erf(x);
-    if (act == ACT_QUICKGELU) return x / (1.0f + ex2_approx(-1.702f * 1.44269504f * x));
-    return x;
+__device__ __forceinline__ float quick_gelu(float x) {   // x * sigmoid(1.702 x)
+    return x / (1.0f + ex2_approx(-1.702f * 1.44269504f * x));
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -111,54 +109,89 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
+// ---- fused LayerNorm (gemm.cuh: Epilogue::ln_*) ----
+// Chan et al.: merge (n_a, mean_a, M2_a) with (n_b, mean_b, M2_b)
+__device__ __forceinline__ void chan_merge(float& n_a, float& mean_a, float& m2_a, float n_b, float mean_b, float m2_b) {
+    const float n = n_a + n_b;
+    const float delta = mean_b - mean_a;
+    const float w = n_b / n;
+    mean_a = fmaf(delta, w, mean_a);
+    m2_a = m2_a + m2_b + delta * delta * n_a * w;
+    n_a = n;
 }
 
-// LayerNorm of NR (1 or 2) complete fp32 rows that other SMs may have written: reads bypass L1 (ld.global.cg).
-// Same arithmetic as kernels::ln_row (two-pass mean / variance over the row held in registers).
-template <int NR>
-__device__ __forceinline__ void ln_rows_from_l2(const float* x, int ld, int nv, int w, const Epilogue& ep, long long row0,
-                                                int lane) {
-    float4 v[NR][8];
-#pragma unroll
-    for (int r = 0; r < NR; ++r)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < nv) v[r][j] = __ldcg(reinterpret_cast<const float4*>(x + (row0 + r) * ld) + lane + 32 * j);
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < nv) s += v[r][j].x + v[r][j].y + v[r][j].z + v[r][j].w;
-        const float mean = warp_sum(s) / (float)w;
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < nv) {
-                const float a = v[r][j].x - mean, b = v[r][j].y - mean, c = v[r][j].z - mean, d = v[r][j].w - mean;
-                q += a * a + b * b + c * c + d * d;
+// Normalise the 32 x (32 * CHUNKS) sub-tile at (row0, col0) that THIS warp wrote one tile ago (same lane -> address mapping
+// as the flush, so its own stores are visible to it), once all column parts of the strip have published their statistics.
+template <int CHUNKS>
+__device__ __forceinline__ void ln_apply_subtile(const Epilogue& ep, int M, int N, int row0, int col0, int nparts, int lane) {
+    const int srow = lane >> 3, sunit = lane & 7;
+    const int* cnt = ep.ln_counters + (row0 >> 5);
+    if (lane == 0) {
+        int seen;
+        uint64_t t0 = 0;
+        uint32_t spins = 0;
+        while (true) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+            if (seen >= nparts) break;
+            if (t0 == 0) t0 = ptx::globaltimer_ns();
+            if ((++spins & 0xff) == 0 && ptx::globaltimer_ns() - t0 > 2000000000ull) {
+                printf("marqo_b200: fused LayerNorm strip %d never completed (%d of %d parts)\n", row0 >> 5, seen, nparts);
+                __trap();
             }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)w + ep.ln_eps);
+        }
+    }
+    __syncwarp();
+    if (ep.ln_debug_skip) return;
+    // lane == row: merge the strip's partial statistics
+    float mean = 0.f, rstd = 0.f;
+    {
+        const int row = row0 + lane;
+        if (row < M) {
+            const float2* st = ep.ln_stats + (size_t)row * LN_MAX_PARTS;
+            const float pn = (float)(N / nparts);
+            float n = 0.f, m2 = 0.f;
+            for (int k = 0; k < nparts; ++k) {
+                const float2 s = __ldcg(st + k);
+                if (k == 0) {
+                    n = pn;
+                    mean = s.x;
+                    m2 = s.y;
+                } else {
+                    chan_merge(n, mean, m2, pn, s.x, s.y);
+                }
+            }
+            rstd = 1.0f / sqrtf(m2 / (float)N + ep.ln_eps);
+        }
+    }
+    const float* xo = reinterpret_cast<const float*>(ep.out);
+#pragma unroll 1
+    for (int c = 0; c < CHUNKS; ++c) {
+        const int col = col0 + c * 32 + sunit * 4;
+        const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col));
+        float4 x[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (j < nv) {
-                const int i4 = lane + 32 * j;
-                const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma) + i4);
-                const float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_beta) + i4);
+        for (int i = 0; i < 8; ++i) {
+            const int row = row0 + i * 4 + srow;
+            x[i] = row < M ? __ldcg(reinterpret_cast<const float4*>(xo + (size_t)row * N + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + srow;
+            const float mu = __shfl_sync(0xffffffffu, mean, rr), rs = __shfl_sync(0xffffffffu, rstd, rr);
+            const int row = row0 + rr;
+            if (row < M) {
                 float4 y;
-                y.x = (v[r][j].x - mean) * rstd * g.x + b.x;
-                y.y = (v[r][j].y - mean) * rstd * g.y + b.y;
-                y.z = (v[r][j].z - mean) * rstd * g.z + b.z;
-                y.w = (v[r][j].w - mean) * rstd * g.w + b.w;
-                if (ep.ln_out_f32) reinterpret_cast<float4*>(ep.ln_out_f32 + (row0 + r) * w)[i4] = y;
+                y.x = (x[i].x - mu) * rs * g.x + b.x;
+                y.y = (x[i].y - mu) * rs * g.y + b.y;
+                y.z = (x[i].z - mu) * rs * g.z + b.z;
+                y.w = (x[i].w - mu) * rs * g.w + b.w;
+                if (ep.ln_out_f32) *reinterpret_cast<float4*>(ep.ln_out_f32 + (size_t)row * N + col) = y;
                 if (ep.ln_out_bf16)
-                    reinterpret_cast<uint2*>(ep.ln_out_bf16 + (row0 + r) * w)[i4] =
+                    *reinterpret_cast<uint2*>(ep.ln_out_bf16 + (size_t)row * N + col) =
                         make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
             }
+        }
     }
 }
 
@@ -325,9 +358,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
                     }
                     __syncwarp();   // every lane has read the bias row: the buffer may be overwritten
-                    if (ep.act != ACT_NONE) {
+                    // one uniform branch per chunk, NOT a per-element select: with `apply_act(f, ep.act)` inside the loop
+                    // the compiler if-converted the switch and every element paid for erf-GELU AND QuickGELU (two ex2 and
+                    // a reciprocal, ~40 instructions per element in the r02 SASS; fc1 was epilogue-bound at 73 % tensor pipe)
+                    if (ep.act == ACT_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    } else if (ep.act == ACT_QUICKGELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -374,12 +413,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // residual GEMMs (fp32 out in this engine) flush after every chunk
         const int chunks_per_flush = (ep.out_fp32 || residual) ? 1 : cols_per_flush / 32;
         const int srow = lane >> 3, sunit = lane & 7;         // coalesced phase: 4 rows x 8 sixteen-byte units per instr
+        const bool ln_on = !GATHER && ep.ln_gamma != nullptr;
+        const int ln_parts = p.N / HALF_COLS;                 // column parts (= statistics writers) per row
+        int pend_row0 = -1, pend_col0 = 0;                    // fused LayerNorm: the sub-tile still to be normalised
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = cluster_id; t < num_super; t += num_clusters) {
             const int m0 = ((t / p.tiles_n) * CLUSTER + (int)crank) * BM;
             const int nt0 = (t % p.tiles_n) * BN + half * HALF_COLS;
             const int wrow0 = m0 + sp * 32;                   // first row of this warp's 32-row band
+            float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;     // fused LayerNorm: this lane's row over this warp's columns
             if (residual && has_cols) {
                 // pull the residual band this warp needs for its NEXT tile towards L2 (the very first tile: itself)
                 for (int pass = (t == cluster_id ? 0 : 1); pass < 2; ++pass) {
@@ -445,9 +488,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
                         f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
                     }
-                    if (ep.act != ACT_NONE) {
+                    if (ep.act == ACT_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], ep.act);
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                    } else if (ep.act == ACT_QUICKGELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
                     }
                     if (ep.rowbias) {   // ViT patch-embed: positional embedding of this lane's patch
                         const int row = wrow0 + lane;
@@ -472,6 +518,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             f[4 * j + 3] += b.w;
                         }
                         __syncwarp();   // everyone has read its residual row before the buffer is overwritten
+                    }
+                    if (ln_on) {   // (mean, M2) of this chunk's 32 values of the lane's row, merged into the running pair
+                        float cs = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cs += f[j];
+                        const float cm = cs * (1.0f / 32.0f);
+                        float cq = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cq = fmaf(f[j] - cm, f[j] - cm, cq);
+                        if (st_n == 0.f) {
+                            st_n = 32.f;
+                            st_mean = cm;
+                            st_m2 = cq;
+                        } else {
+                            chan_merge(st_n, st_mean, st_m2, 32.f, cm, cq);
+                        }
                     }
                     // (3) own row -> staging buffer (swizzled 16-byte units)
                     if (ep.out_fp32) {
@@ -515,33 +577,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     __syncwarp();
                 }
             }
-            if (!GATHER && ep.ln_gamma != nullptr && has_cols && wrow0 < p.M) {
-                // fused LayerNorm: count the strip's writers and let the last one normalise.  One acq_rel atomic per
-                // warp publishes the whole warp's stores (they are ordered before it by the warp barrier) and, in the
-                // last writer, acquires everybody else's.  NOT __threadfence(): that is fence.sc.gpu, and 16 k
-                // sequentially-consistent fences per launch serialise across the GPU (measured: 33 -> 74 ms per step).
-                __syncwarp();
-                int old = 0;
-                if (lane == 0)
-                    asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;"
-                                 : "=r"(old) : "l"(ep.ln_counters + (wrow0 >> 5)) : "memory");
-                old = __shfl_sync(0xffffffffu, old, 0);
-                if (old == 2 * p.tiles_n - 1) {
-                    if (lane == 0) ep.ln_counters[wrow0 >> 5] = 0;   // ready for the next launch
-                    const float* xo = reinterpret_cast<const float*>(ep.out);
-                    const int nv = p.N >> 7;
-                    const int nrows = min(32, p.M - wrow0);
-                    int rr = 0;
-#pragma unroll 1
-                    for (; rr + 2 <= nrows; rr += 2) ln_rows_from_l2<2>(xo, ep.ldo, nv, p.N, ep, wrow0 + rr, lane);
-                    if (rr < nrows) ln_rows_from_l2<1>(xo, ep.ldo, nv, p.N, ep, wrow0 + rr, lane);
+            if (!GATHER && ln_on) {
+                const bool contributes = has_cols && nt0 < p.N && wrow0 < p.M;
+                if (contributes) {
+                    // publish this warp's per-row statistics, then count the strip's writers.  One release atomic per warp
+                    // covers the whole warp's stores (they are ordered before it by the warp barrier).  NOT
+                    // __threadfence(): that is fence.sc.gpu.
+                    const int row = wrow0 + lane;
+                    if (row < p.M) ep.ln_stats[(size_t)row * LN_MAX_PARTS + nt0 / HALF_COLS] = make_float2(st_mean, st_m2);
+                    __syncwarp();
+                    if (lane == 0)
+                        asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ep.ln_counters + (wrow0 >> 5)) : "memory");
                 }
+                // the sub-tile written one tile ago: its strip has had a whole tile's time to complete
+                if (pend_row0 >= 0) ln_apply_subtile<CHUNKS>(ep, p.M, p.N, pend_row0, pend_col0, ln_parts, lane);
+                pend_row0 = contributes ? wrow0 : -1;
+                pend_col0 = nt0;
             }
+            if (!GATHER && ep.ln_zero != nullptr && half == 0 && nt0 == 0 && lane == 0 && wrow0 < p.M)
+                ep.ln_zero[wrow0 >> 5] = 0;   // the other counter array: ready for the next fused GEMM
             if (++acc == ACC_STAGES) {
                 acc = 0;
                 acc_phase ^= 1;
             }
         }
+        if (!GATHER && ln_on && pend_row0 >= 0) ln_apply_subtile<CHUNKS>(ep, p.M, p.N, pend_row0, pend_col0, ln_parts, lane);
     } else if (GATHER && warp >= 2 + EW) {
         // ---------------------------------------------------------------- patch gather (uint8 HWC -> bf16 A stage)
         // Warp gw owns rows gw*32 .. gw*32+31 of this CTA's 128-row A tile: lane == patch.  Per patch pixel row dy the
@@ -733,7 +793,7 @@ void launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int 
     if (lda % 8 != 0 || ep.ldo % 8 != 0) fail(B200_ERR_INTERNAL, "gemm: leading dimensions must be multiples of 8");
     if (ep.ln_gamma != nullptr) {
         if (!ep.out_fp32 || ep.ldo != N || N % 128 != 0 || N > 1024 || ep.remap_group != 0 || !ep.ln_beta ||
-            !ep.ln_counters || (!ep.ln_out_bf16 && !ep.ln_out_f32))
+            !ep.ln_counters || !ep.ln_stats || (!ep.ln_out_bf16 && !ep.ln_out_f32))
             fail(B200_ERR_INTERNAL, "gemm: fused LayerNorm needs a compact fp32 output of width N %% 128 == 0, N <= 1024");
     }
     configure();
