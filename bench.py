@@ -3,8 +3,9 @@
 
 Headline workload (BASELINE.json `metric`): open_clip/ViT-L-14 image vectorise, batch 256 per GPU, synthetic
 224x224 uint8 RGB, random-init weights of that architecture.  One "step" = one pass of the hot path over one batch:
-uint8 pixels -> ToTensor/Normalize fused im2col -> ViT-L-14 (tcgen05 GEMMs, fused epilogues) -> projection ->
-L2-normalised fp32 embeddings.  Weak scaling: every rank encodes its own batch of 256 (doc-sharded, no collective).
+uint8 pixels -> patch-embed GEMM whose gather warps read the pixels, apply ToTensor/Normalize and fill the tcgen05 A
+operand in shared memory (no patch matrix in HBM) -> ViT-L-14 (tcgen05 GEMMs with fused epilogues, one-shot tcgen05
+attention with P in TMEM) -> projection -> L2-normalised fp32 embeddings.  Weak scaling: every rank encodes its own batch of 256 (doc-sharded, no collective).
 
 Blocks in the same JSON line (all driver-visible):
   topk     exact top-10 of 64 queries over a 10 M x 768 fp16 corpus row-sharded across the ranks; the per-shard blocks

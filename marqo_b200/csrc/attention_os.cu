@@ -121,8 +121,10 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], int c, int kh
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
         const float s0 = __uint_as_float(v[i]), s1 = __uint_as_float(v[i + 1]);
-        float p0 = ex2(fmaf(s0, scale_log2e, -m_safe));
-        float p1 = ex2(fmaf(s1, scale_log2e, -m_safe));
+        // (the clamp only matters for a score more than 2^132 above the first-chunk maximum: it keeps P, l and O far inside fp32 range — such a
+        // key then simply takes the whole row — instead of producing inf / NaN)
+        float p0 = ex2(fminf(fmaf(s0, scale_log2e, -m_safe), 100.0f));
+        float p1 = ex2(fminf(fmaf(s1, scale_log2e, -m_safe), 100.0f));
         if (!FULL) {
             p0 = (c * 32 + i < khi) ? p0 : 0.f;
             p1 = (c * 32 + i + 1 < khi) ? p1 : 0.f;
@@ -462,7 +464,7 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 // ---- ONE pass over S.  softmax(s) = exp2(s' - ref) / sum exp2(s' - ref) for ANY reference, so the
                 // exponent reference does not have to be the row maximum — only close enough that nothing overflows:
                 // ref = (maximum of the row's first 32 scores) + 32.  A later score may exceed that maximum by up to
-                // 2^159 before exp2 overflows, scores more than 2^94 below it flush to zero next to a term >= 2^-32, and
+                // 2^132 before the clamp in exp_chunk engages (l and O stay far inside fp32 range), scores more than 2^94 below it flush to zero next to a term >= 2^-32, and
                 // P, l and O are floating point (bf16 / fp32: 8 exponent bits), so the common factor 2^-32 costs no
                 // precision; it cancels in O / l.  (attention_tc.cu needs the running maximum because it accumulates
                 // over key blocks; here all 256 keys are in TMEM at once.)

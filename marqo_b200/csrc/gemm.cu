@@ -100,6 +100,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return fmaf(hx, e, hx);
 }
 
+// The same erf-GELU on TWO elements per instruction (HFMA2 / ex2.approx.f16x2), for outputs that are rounded to bf16 anyway
+// (fc1's epilogue: the r02 profile had it at 16 fp32 instructions per element and the GEMM epilogue-bound at 75 % tensor
+// pipe).  fp16 has 11 significand bits against bf16's 8: the result carries ~1e-3 relative error before the bf16 rounding
+// of 4e-3 (tests/test_kernels_gpu.py::test_gemm_epilogues; the reference's own CUDA path evaluates GELU in fp16 under
+// torch.autocast, open_clip_model.py:256-258).  |x| up to 360 keeps a * a inside fp16 range.
+__device__ __forceinline__ __half2 gelu_erf_h2(__half2 x) {
+    const __half2 a = __hmul2(x, __float2half2_rn(0.70710678118654752440f));
+    const __half2 t = __habs2(a);
+    const __half2 s = __hmul2(a, a);
+    __half2 r = __hfma2(__float2half2_rn(-2.49374837e-5f), t, __float2half2_rn(5.52836593e-4f));
+    const __half2 u = __hfma2(__float2half2_rn(-5.60337594e-3f), t, __float2half2_rn(3.49920232e-2f));
+    r = __hfma2(r, s, u);
+    r = __hfma2(r, t, __float2half2_rn(-1.54047912e-1f));
+    r = __hfma2(r, t, __float2half2_rn(-9.15890168e-1f));
+    r = __hfma2(r, t, __float2half2_rn(-1.85700115e-1f));
+    r = __hfma2(r, t, __hmul2(t, __float2half2_rn(-1.44269504f)));
+    const __half2 e = h2exp2(r);
+    const __half2 om = __hsub2(__float2half2_rn(1.0f), e);
+    // copysign(1 - e, a) on both halves
+    const uint32_t eb = (*reinterpret_cast<const uint32_t*>(&om) & 0x7fff7fffu) | (*reinterpret_cast<const uint32_t*>(&a) & 0x80008000u);
+    const __half2 erfv = *reinterpret_cast<const __half2*>(&eb);
+    const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+    return __hfma2(hx, erfv, hx);
+}
+
 __device__ __forceinline__ float quick_gelu(float x) {   // x * sigmoid(1.702 x)
     return x / (1.0f + ex2_approx(-1.702f * 1.44269504f * x));
 }
@@ -149,47 +174,56 @@ __device__ __forceinline__ void ln_apply_subtile(const Epilogue& ep, int M, int 
         if (row < M) {
             const float2* st = ep.ln_stats + (size_t)row * LN_MAX_PARTS;
             const float pn = (float)(N / nparts);
-            float n = 0.f, m2 = 0.f;
-            for (int k = 0; k < nparts; ++k) {
-                const float2 s = __ldcg(st + k);
-                if (k == 0) {
-                    n = pn;
-                    mean = s.x;
-                    m2 = s.y;
-                } else {
-                    chan_merge(n, mean, m2, pn, s.x, s.y);
-                }
-            }
+            float2 sv[LN_MAX_PARTS];   // all parts in flight at once (one L2 round trip), then the merge chain
+#pragma unroll
+            for (int k = 0; k < LN_MAX_PARTS; ++k)
+                if (k < nparts) sv[k] = __ldcg(st + k);
+            float n = pn, m2 = sv[0].y;
+            mean = sv[0].x;
+#pragma unroll
+            for (int k = 1; k < LN_MAX_PARTS; ++k)
+                if (k < nparts) chan_merge(n, mean, m2, pn, sv[k].x, sv[k].y);
             rstd = 1.0f / sqrtf(m2 / (float)N + ep.ln_eps);
         }
     }
     const float* xo = reinterpret_cast<const float*>(ep.out);
+    // two 32-column chunks per step: 16 independent 16-byte loads in flight per lane (the epilogue has only 8 warps per SM,
+    // so memory-level parallelism has to come from each of them)
+    constexpr int STEP = CHUNKS >= 2 ? 2 : 1;
 #pragma unroll 1
-    for (int c = 0; c < CHUNKS; ++c) {
-        const int col = col0 + c * 32 + sunit * 4;
-        const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col));
-        float4 x[8];
+    for (int c = 0; c < CHUNKS; c += STEP) {
+        float4 x[STEP][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = row0 + i * 4 + srow;
-            x[i] = row < M ? __ldcg(reinterpret_cast<const float4*>(xo + (size_t)row * N + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int cc = 0; cc < STEP; ++cc) {
+            const int col = col0 + (c + cc) * 32 + sunit * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = row0 + i * 4 + srow;
+                x[cc][i] = row < M ? __ldcg(reinterpret_cast<const float4*>(xo + (size_t)row * N + col))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + srow;
-            const float mu = __shfl_sync(0xffffffffu, mean, rr), rs = __shfl_sync(0xffffffffu, rstd, rr);
-            const int row = row0 + rr;
-            if (row < M) {
-                float4 y;
-                y.x = (x[i].x - mu) * rs * g.x + b.x;
-                y.y = (x[i].y - mu) * rs * g.y + b.y;
-                y.z = (x[i].z - mu) * rs * g.z + b.z;
-                y.w = (x[i].w - mu) * rs * g.w + b.w;
-                if (ep.ln_out_f32) *reinterpret_cast<float4*>(ep.ln_out_f32 + (size_t)row * N + col) = y;
-                if (ep.ln_out_bf16)
-                    *reinterpret_cast<uint2*>(ep.ln_out_bf16 + (size_t)row * N + col) =
-                        make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        for (int cc = 0; cc < STEP; ++cc) {
+            const int col = col0 + (c + cc) * 32 + sunit * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + col));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + col));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + srow;
+                const float mu = __shfl_sync(0xffffffffu, mean, rr), rs = __shfl_sync(0xffffffffu, rstd, rr);
+                const int row = row0 + rr;
+                if (row < M) {
+                    float4 y;
+                    y.x = (x[cc][i].x - mu) * rs * g.x + b.x;
+                    y.y = (x[cc][i].y - mu) * rs * g.y + b.y;
+                    y.z = (x[cc][i].z - mu) * rs * g.z + b.z;
+                    y.w = (x[cc][i].w - mu) * rs * g.w + b.w;
+                    if (ep.ln_out_f32) *reinterpret_cast<float4*>(ep.ln_out_f32 + (size_t)row * N + col) = y;
+                    if (ep.ln_out_bf16)
+                        *reinterpret_cast<uint2*>(ep.ln_out_bf16 + (size_t)row * N + col) =
+                            make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+                }
             }
         }
     }
@@ -361,18 +395,29 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     // one uniform branch per chunk, NOT a per-element select: with `apply_act(f, ep.act)` inside the loop
                     // the compiler if-converted the switch and every element paid for erf-GELU AND QuickGELU (two ex2 and
                     // a reciprocal, ~40 instructions per element in the r02 SASS; fc1 was epilogue-bound at 73 % tensor pipe)
-                    if (ep.act == ACT_GELU) {
+                    uint32_t pk[16];
+                    if (ep.act == ACT_GELU && !ep.act_fp32) {
+                        // packed-half erf-GELU: two elements per instruction
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-                    } else if (ep.act == ACT_QUICKGELU) {
+                        for (int j = 0; j < 16; ++j) {
+                            const float2 y = __half22float2(gelu_erf_h2(__floats2half2_rn(f[2 * j], f[2 * j + 1])));
+                            pk[j] = pack_bf16x2(y.x, y.y);
+                        }
+                    } else {
+                        if (ep.act == ACT_GELU) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+                            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+                        } else if (ep.act == ACT_QUICKGELU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
                     }
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         *reinterpret_cast<uint4*>(stage_buf + lane * 64 + ((j ^ wswz) << 4)) =
-                            make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                       pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
                     __syncwarp();
                     const int col = n0 + funit * 8;
 #pragma unroll
@@ -423,7 +468,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int nt0 = (t % p.tiles_n) * BN + half * HALF_COLS;
             const int wrow0 = m0 + sp * 32;                   // first row of this warp's 32-row band
             float st_n = 0.f, st_mean = 0.f, st_m2 = 0.f;     // fused LayerNorm: this lane's row over this warp's columns
-            if (residual && has_cols) {
+            // (not for long K: a tile of fc2, K = 4096, takes ~28 us during which ~80 MB stream through the L2 — the lines
+            // were evicted again before their use and the residual was fetched from HBM twice: r01/r02 ncu 1.32 GB per
+            // launch against 1.085 GB algorithmic.  Its epilogue has four times the slack to take the HBM latency itself.)
+            if (residual && has_cols && p.K <= 2048) {
                 // pull the residual band this warp needs for its NEXT tile towards L2 (the very first tile: itself)
                 for (int pass = (t == cluster_id ? 0 : 1); pass < 2; ++pass) {
                     const int tn = t + pass * num_clusters;
@@ -589,7 +637,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     if (lane == 0)
                         asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(ep.ln_counters + (wrow0 >> 5)) : "memory");
                 }
-                // the sub-tile written one tile ago: its strip has had a whole tile's time to complete
+                // the sub-tile written one tile ago: its strip has had a whole tile's time to complete.  (Doing this before
+                // the wait for the next accumulator instead — "in the idle time" — measured slower: 46.5 vs 44.5 ms per step
+                // with fc2 fused, because it delays the epilogue whenever the accumulator is already there.)
                 if (pend_row0 >= 0) ln_apply_subtile<CHUNKS>(ep, p.M, p.N, pend_row0, pend_col0, ln_parts, lane);
                 pend_row0 = contributes ? wrow0 : -1;
                 pend_col0 = nt0;

@@ -16,6 +16,7 @@ struct Epilogue {
     const float* residual = nullptr;  // fp32 [M, ldr], added after the activation
     int ldr = 0;
     int act = ACT_NONE;
+    int act_fp32 = 0;     // 1: evaluate erf-GELU in fp32 even for a bf16 output (default: packed fp16, see gemm.cu gelu_erf_h2)
     void* out = nullptr;  // bf16 or fp32 [*, ldo]
     int ldo = 0;
     int out_fp32 = 0;

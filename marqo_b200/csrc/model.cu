@@ -279,18 +279,24 @@ void attend(b200_model* m, Counter& c, int B, int S, int w, int heads, int mask_
 }
 
 // LayerNorm fused into the producing residual GEMM's epilogue (gemm.cuh: Epilogue::ln_*).  OFF by default: correct
-// (tests/test_kernels_gpu.py::test_gemm_fused_layernorm, the encoder parity tests pass with it), but the "last writer
-// of a 32-row strip normalises it" scheme concentrates the LayerNorm work on whichever CTA pair finishes a row band
-// last, and that pair then starts its next tile late and is last again: measured on ViT-L-14 b256 the GEMMs go from
-// 33.4 to 72 ms per step (fc2: 0.375 -> 1.175 ms, tensor pipe 91 % -> 35 %, profiles/r02_ncu_summary.md §5), while the
-// counters alone cost nothing (42.5 ms per step with the normalisation skipped vs 44.4 ms with the separate launches).
-// MARQO_B200_LN_FUSION=1 enables it for experiments.
-bool ln_fusion_enabled() {
-    static const bool on = [] {
-        const char* e = getenv("MARQO_B200_LN_FUSION");
-        return e != nullptr && e[0] == '1';
-    }();
+// (tests/test_kernels_gpu.py::test_gemm_fused_layernorm; the encoder parity tests pass with MARQO_B200_LN_FUSION=1 / 2),
+// and the publish + count part is free (40.2 ms per step with the normalisation skipped vs 42.1 with separate launches),
+// but re-reading the rows through the GEMM's 8 epilogue warps per SM is latency-bound where the standalone kernel runs at
+// the HBM roofline: ViT-L-14 b256, same box, 43.5-44.3 ms (separate) / 44.5 (fc2 fused) / 46.9 (both fused);
+// profiles/r02_ncu_summary.md §5-6 has the two schemes that were tried and their profiles.
+// MARQO_B200_GELU_FP32=1: evaluate fc1's erf-GELU in fp32 instead of packed fp16 (A/B timing and accuracy comparisons)
+bool gelu_fp32() {
+    static const bool on = getenv("MARQO_B200_GELU_FP32") != nullptr;
     return on;
+}
+
+// 0 = separate launches, 1 = out_proj and fc2 fused, 2 = fc2 only (K = 4 * width: its epilogue has four times the slack)
+int ln_fusion_mode() {
+    static const int mode = [] {
+        const char* e = getenv("MARQO_B200_LN_FUSION");
+        return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 0;
+    }();
+    return mode;
 }
 
 // which: 0 = out_proj (counter array A, zeroes B), 1 = fc2 (counter array B, zeroes A).  The two residual GEMMs of a layer
@@ -315,7 +321,8 @@ void fuse_ln(b200_model* m, gemm::Epilogue& e, int which, const float* gamma, co
 void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, int mask_mode) {
     const int M = B * S, w = T.d.width, mlp = T.d.mlp;
     const int act = m->desc.act == B200_ACT_QUICKGELU ? gemm::ACT_QUICKGELU : gemm::ACT_GELU;
-    const bool fused = ln_fusion_enabled();
+    const int fmode = ln_fusion_mode();
+    const bool fused = fmode != 0, fused_o = fmode == 1;
     for (size_t li = 0; li < T.layers.size(); ++li) {
         const LayerW& L = T.layers[li];
         if (!fused || li == 0) {
@@ -335,9 +342,10 @@ void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, i
         e2.out = m->x;
         e2.ldo = w;
         e2.out_fp32 = 1;
-        if (fused) fuse_ln(m, e2, 0, L.ln2_w, L.ln2_b, 1e-5f, nullptr, m->h);
+        if (fused_o) fuse_ln(m, e2, 0, L.ln2_w, L.ln2_b, 1e-5f, nullptr, m->h);
+        else if (fused) e2.ln_zero = m->ln_counters + m->ln_counter_stride;   // re-arm fc2's counters
         linear(m, c, m->o, M, w, L.w_o, w, e2);
-        if (!fused) {
+        if (!fused_o) {
             kernels::layernorm(m->x, w, L.ln2_w, L.ln2_b, 1e-5f, M, w, nullptr, m->h, m->stream);
             ++c.n;
         }
@@ -346,6 +354,7 @@ void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, i
         e3.act = act;
         e3.out = m->u;
         e3.ldo = mlp;
+        e3.act_fp32 = gelu_fp32() ? 1 : 0;
         linear(m, c, m->h, M, w, L.w_fc, mlp, e3);
         gemm::Epilogue e4;
         e4.bias = L.b_proj;
@@ -367,7 +376,8 @@ void run_clip_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S, i
 void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
     const int M = B * S, w = T.d.width, mlp = T.d.mlp;
     const float eps = 1e-12f;
-    const bool fused = ln_fusion_enabled();
+    const int fmode = ln_fusion_mode();
+    const bool fused = fmode != 0, fused_o = fmode == 1;
     for (const LayerW& L : T.layers) {
         gemm::Epilogue e1;
         e1.bias = L.b_qkv;
@@ -382,9 +392,10 @@ void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
         e2.out = m->x;
         e2.ldo = w;
         e2.out_fp32 = 1;
-        if (fused) fuse_ln(m, e2, 0, L.ln1_w, L.ln1_b, eps, m->x, m->h);
+        if (fused_o) fuse_ln(m, e2, 0, L.ln1_w, L.ln1_b, eps, m->x, m->h);
+        else if (fused) e2.ln_zero = m->ln_counters + m->ln_counter_stride;   // re-arm fc2's counters
         linear(m, c, m->o, M, w, L.w_o, w, e2);
-        if (!fused) {
+        if (!fused_o) {
             kernels::layernorm(m->x, w, L.ln1_w, L.ln1_b, eps, M, w, m->x, m->h, m->stream);
             ++c.n;
         }
@@ -393,6 +404,7 @@ void run_bert_blocks(b200_model* m, Counter& c, const TowerW& T, int B, int S) {
         e3.act = gemm::ACT_GELU;
         e3.out = m->u;
         e3.ldo = mlp;
+        e3.act_fp32 = gelu_fp32() ? 1 : 0;
         linear(m, c, m->h, M, w, L.w_fc, mlp, e3);
         gemm::Epilogue e4;
         e4.bias = L.b_proj;
