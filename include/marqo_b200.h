@@ -276,7 +276,10 @@ int b200_model_finalize(b200_model* m);
 /* Images as uint8 HWC (host), all n of size h x w: resize (bicubic, shortest side) ->
  * centre-crop -> /255 -> Normalize -> ViT -> proj -> optional L2 normalise.
  * Replaces preprocessors['image'](pil).to(device) (src/marqo/tensor_search/add_docs.py:129-134)
- * + OPEN_CLIP.encode_image (open_clip_model.py:249-266).  out: fp32 host [n, embed_dim]. */
+ * + OPEN_CLIP.encode_image (open_clip_model.py:249-266).  out: fp32 host [n, embed_dim].
+ * The /255 and Normalize steps happen inside the patch-embedding GEMM's operand load (its gather warps read the uint8
+ * pixels and write bf16 into the tensor core's shared-memory operand): no normalised image or patch matrix exists in HBM
+ * (images already of the model's size skip the resize pass as well). */
 int b200_model_encode_images_u8(b200_model* m, const uint8_t* hwc, int n, int h, int w, int normalize,
                                 float* out);
 /* Already-preprocessed fp32 CHW tensors [n,3,S,S] (the reference passes these through

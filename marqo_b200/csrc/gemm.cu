@@ -43,7 +43,10 @@ struct Cfg {
     // per epilogue warp: a 32-row transpose buffer (128-byte rows; 64-byte rows for EW = 16) + a 128-byte bias row
     static constexpr uint32_t EPI_ROW_BYTES = EW == 16 ? 64 : 128;
     // (EW = 16 keeps the bias row inside the transpose buffer, so the smem ring stays 6 stages deep at BN = 256)
-    static constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_ROW_BYTES + (EW == 16 ? 0 : 128);
+    // (+ for the general epilogue of a GEMM that can have a residual input: a second 32 x 128 B buffer the NEXT chunk's
+    //  residual block is prefetched into with cp.async while the current chunk is processed)
+    static constexpr uint32_t RES_BYTES = (EW == 8 && !GATHER) ? 32 * 128 : 0;
+    static constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_ROW_BYTES + (EW == 16 ? 0 : 128) + RES_BYTES;
     static constexpr uint32_t EPI_BYTES = EW * EPI_WARP_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - (int)EPI_BYTES - (int)RAW_BYTES) / (int)STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -452,6 +455,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const float* const residual = GATHER ? nullptr : ep.residual;   // the patch-embed GEMM has no residual input
         uint8_t* stage_buf = smem_epi + (size_t)(warp - 2) * C::EPI_WARP_BYTES;
         float* bias_row = reinterpret_cast<float*>(stage_buf + 32 * 128);
+        uint8_t* res_buf = stage_buf + 32 * 128 + 128;        // residual block of the chunk about to be processed (cp.async)
         const int esz = ep.out_fp32 ? 4 : 2;                  // output element size
         const int cols_per_flush = 128 / esz;                 // 32 fp32 or 64 bf16 columns fill a 128-byte row
         // bf16 results are staged two chunks (64 columns) per flush; a residual block occupies the whole buffer, so
@@ -461,8 +465,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const bool ln_on = !GATHER && ep.ln_gamma != nullptr;
         const int ln_parts = p.N / HALF_COLS;                 // column parts (= statistics writers) per row
         int pend_row0 = -1, pend_col0 = 0;                    // fused LayerNorm: the sub-tile still to be normalised
+        // Residual blocks travel global -> shared memory asynchronously, one chunk AHEAD of their use (and across the
+        // tile boundary: the next tile's first block is requested before this warp waits for that accumulator), in the
+        // swizzled layout the lane == row read expects.  The r02 profile had out_proj (K = 1024: a tile every ~7 us) at
+        // 44-47 % tensor pipe with its 8 epilogue warps taking one exposed L2 round trip per 32-column chunk.
+        int pref_t = -1, pref_c = -1;   // the (tile, chunk) whose residual block is in res_buf / on its way there
+        auto prefetch_residual = [&](int tt, int cc) {
+            if (GATHER || !residual || !has_cols || tt >= num_super) return;
+            const int pm0 = ((tt / p.tiles_n) * CLUSTER + (int)crank) * BM + sp * 32;
+            const int pn0 = (tt % p.tiles_n) * BN + half * HALF_COLS + cc * 32;
+            if (pn0 >= p.N) return;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + srow;
+                const bool ok = pm0 + rr < p.M;
+                const float* src = ok ? residual + (size_t)(pm0 + rr) * ep.ldr + pn0 + sunit * 4 : residual;
+                const uint32_t dst = ptx::smem_u32(res_buf + rr * 128 + ((sunit ^ (rr & 7)) << 4));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            pref_t = tt;
+            pref_c = cc;
+        };
         int acc = 0;
         uint32_t acc_phase = 0;
+        prefetch_residual(cluster_id, 0);
         for (int t = cluster_id; t < num_super; t += num_clusters) {
             const int m0 = ((t / p.tiles_n) * CLUSTER + (int)crank) * BM;
             const int nt0 = (t % p.tiles_n) * BN + half * HALF_COLS;
@@ -496,15 +523,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 //     the 32 x 32 fp32 residual block in coalesced order (4 rows x 128 B per instruction)
                 float bias_v = 0.f;
                 if (ep.bias && cols_ok) bias_v = __ldg(ep.bias + n0 + lane);
-                float4 rres[8];
-                if (residual && cols_ok) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int rr = wrow0 + i * 4 + srow;
-                        rres[i] = rr < p.M ? *reinterpret_cast<const float4*>(residual + (size_t)rr * ep.ldr + n0 + sunit * 4)
-                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
                 // (2) accumulator chunk: lane == row
                 uint32_t v[32];
                 if (has_cols) {
@@ -520,11 +538,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 if (cols_ok) {
                     bias_row[lane] = bias_v;
                     if (residual) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int rr = i * 4 + srow;
-                            *reinterpret_cast<float4*>(stage_buf + rr * 128 + ((sunit ^ (rr & 7)) << 4)) = rres[i];
-                        }
+                        // normally requested one chunk ago; a warp whose previous tile had no columns asks now
+                        if (pref_t != t || pref_c != c) prefetch_residual(t, c);
+                        asm volatile("cp.async.wait_group 0;" ::: "memory");
                     }
                     __syncwarp();
                     float f[32];
@@ -559,13 +575,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     if (residual) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 b = *reinterpret_cast<const float4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                            const float4 b = *reinterpret_cast<const float4*>(res_buf + lane * 128 + ((j ^ (lane & 7)) << 4));
                             f[4 * j] += b.x;
                             f[4 * j + 1] += b.y;
                             f[4 * j + 2] += b.z;
                             f[4 * j + 3] += b.w;
                         }
-                        __syncwarp();   // everyone has read its residual row before the buffer is overwritten
+                        __syncwarp();   // everyone has read its residual row: request the next block into the same buffer
+                        if (c + 1 < CHUNKS) prefetch_residual(t, c + 1);
+                        else prefetch_residual(t + num_clusters, 0);
                     }
                     if (ln_on) {   // (mean, M2) of this chunk's 32 values of the lane's row, merged into the running pair
                         float cs = 0.f;
