@@ -43,7 +43,6 @@ constexpr uint32_t SMEM_BYTES = 2 * Q_BYTES + 2 * KV_BYTES + 2 * TAIL_BYTES + BA
 static_assert(SMEM_BYTES <= 115712, "two CTAs per SM");
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t S_COL = 0, P_COL = 0, O_COL = 128;
-constexpr int DEFAULT_ISSUE = 0;
 constexpr uint32_t T_COL = 192;   // remainder key's scores (N = 16 MMA, column 0 is the key), written after S is consumed
 
 __device__ __forceinline__ float ex2(float x) {
@@ -136,11 +135,10 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&v)[32], int c, int kh
     tmem_st_32x32b_x16(p_addr + 16 * c, pk);
 }
 
-// ISSUE = 0: warp 1 issues every tcgen05.mma and is told "P is complete" / "O has been read" through mbarriers.
-// ISSUE = 1: the softmax warps synchronise among themselves with a 128-thread named barrier and ONE of their threads issues
-//            P V (+ the remainder-key MMA) and the next item's S itself — two mbarrier hand-offs through another warp
-//            (arrive -> that warp's try_wait wakes up -> issue) less on the item's serial chain.
-template <int MASK, int ISSUE>
+// (Tried and measured slower, 200 vs 176 us per ViT-L-14 layer in one run: letting an elected softmax thread issue P V and the
+//  next item's S itself after a 128-thread named barrier, to save the two mbarrier hand-offs through warp 1 — the issuing
+//  thread's waits and the divergence they cause inside its warp cost more than the hops.)
+template <int MASK>
 __global__ void __launch_bounds__(THREADS, 2)
 attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
                     const __nv_bfloat16* __restrict__ qkv,
@@ -277,18 +275,16 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ================================================================== MMA issuer (ISSUE == 0)
-        if (ISSUE == 0) {
-            uint32_t n = 0, uc = 0;
-            for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++uc) {
-                for (int qb = 0; qb < q_blocks; ++qb, ++n) {
-                    if (n > 0) ptx::mbar_wait(tmem_free, (n - 1) & 1);   // the previous item's O has been read out
-                    if (lane == 0) issue_s(n, uc, qb);
-                    __syncwarp();
-                    ptx::mbar_wait(p_full, n & 1);       // P of this item is in TMEM (and S fully consumed)
-                    if (lane == 0) issue_pv(n, uc, qb);
-                    __syncwarp();
-                }
+        // ================================================================== MMA issuer
+        uint32_t n = 0, uc = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++uc) {
+            for (int qb = 0; qb < q_blocks; ++qb, ++n) {
+                if (n > 0) ptx::mbar_wait(tmem_free, (n - 1) & 1);   // the previous item's O has been read out
+                if (lane == 0) issue_s(n, uc, qb);
+                __syncwarp();
+                ptx::mbar_wait(p_full, n & 1);       // P of this item is in TMEM (and S fully consumed)
+                if (lane == 0) issue_pv(n, uc, qb);
+                __syncwarp();
             }
         }
     } else if (warp == 6) {
@@ -458,11 +454,8 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         const int sp = warp & 3;
         const int r = sp * 32 + lane;
         const uint32_t lane_addr = tmem_base + (uint32_t(sp * 32) << 16);
-        uint32_t n = 0, uc = 0;
-        const bool issuer = ISSUE == 1 && warp == 2 && lane == 0;
-        if (issuer && (int)blockIdx.x < total_units) issue_s(0, 0, 0);
-        if (ISSUE == 1) __syncwarp();
-        for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++uc) {
+        uint32_t n = 0;
+        for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
             const int b = u / H, h = u - b * H;
             const int row_base = b * S;
             int len = S;
@@ -511,14 +504,8 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 float m_run = m_run0;
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
-                if (ISSUE == 1) {
-                    ptx::bar_sync<1, 128>();             // every row's P is in TMEM
-                    if (issuer) issue_pv(n, uc, qb);
-                    __syncwarp();
-                } else {
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(p_full);
-                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(p_full);
                 ptx::mbar_wait(o_full, n & 1);
                 ptx::tc_fence_after();
                 ptx::tmem_ld_32x32b_x32(lane_addr + O_COL, va);
@@ -528,17 +515,8 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 ptx::tmem_ld_wait();
                 // O is in registers: the next item's S may overwrite the accumulator columns
                 ptx::tc_fence_before();
-                if (ISSUE == 1) {
-                    ptx::bar_sync<1, 128>();
-                    if (issuer) {
-                        if (qb + 1 < q_blocks) issue_s(n + 1, uc, qb + 1);
-                        else if (u + (int)gridDim.x < total_units) issue_s(n + 1, uc + 1, 0);
-                    }
-                    __syncwarp();
-                } else {
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(tmem_free);
-                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(tmem_free);
                 // ---- remainder key: online update of (m, l); folded into the output below
                 float t_alpha = 1.f, t_p = 0.f;
                 if (has_tail_key) {
@@ -614,10 +592,8 @@ int launch_os(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     static std::once_flag once;
     std::call_once(once, [] {
         const auto attr = cudaFuncAttributeMaxDynamicSharedMemorySize;
-        MB_CUDA(cudaFuncSetAttribute(os::attention_os_kernel<MASK_NONE, 0>, attr, (int)os::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(os::attention_os_kernel<MASK_KEYLEN, 0>, attr, (int)os::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(os::attention_os_kernel<MASK_NONE, 1>, attr, (int)os::SMEM_BYTES));
-        MB_CUDA(cudaFuncSetAttribute(os::attention_os_kernel<MASK_KEYLEN, 1>, attr, (int)os::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(os::attention_os_kernel<MASK_NONE>, attr, (int)os::SMEM_BYTES));
+        MB_CUDA(cudaFuncSetAttribute(os::attention_os_kernel<MASK_KEYLEN>, attr, (int)os::SMEM_BYTES));
     });
     CUtensorMap tmap = make_tmap_2d(qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (uint64_t)3 * W, (uint64_t)B * S,
                                     (uint64_t)3 * W * 2, os::HD, os::BQ, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -631,17 +607,12 @@ int launch_os(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     const int s_main = tail ? os::NK : S;
     const int total_units = B * H;
     const int grid = std::min(2 * sm_count(device), total_units);
-    // MARQO_B200_ATTN_ISSUE=0 keeps the dedicated MMA-issuer warp (A/B timing)
-    static const int issue_mode = [] {
-        const char* e = getenv("MARQO_B200_ATTN_ISSUE");
-        return (e && (e[0] == '0' || e[0] == '1')) ? e[0] - '0' : os::DEFAULT_ISSUE;
-    }();
-    using Fn = void (*)(const CUtensorMap, const CUtensorMap, const __nv_bfloat16*, __nv_bfloat16*, int, int, int, const int32_t*,
-                        float, int, int, int);
-    static const Fn table[2][2] = {{os::attention_os_kernel<MASK_NONE, 0>, os::attention_os_kernel<MASK_NONE, 1>},
-                                   {os::attention_os_kernel<MASK_KEYLEN, 0>, os::attention_os_kernel<MASK_KEYLEN, 1>}};
-    table[mask == MASK_NONE ? 0 : 1][issue_mode]<<<grid, os::THREADS, os::SMEM_BYTES, stream>>>(
-        tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
+    if (mask == MASK_NONE)
+        os::attention_os_kernel<MASK_NONE><<<grid, os::THREADS, os::SMEM_BYTES, stream>>>(
+            tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
+    else
+        os::attention_os_kernel<MASK_KEYLEN><<<grid, os::THREADS, os::SMEM_BYTES, stream>>>(
+            tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
     MB_CUDA(cudaGetLastError());
     return 1;
 }

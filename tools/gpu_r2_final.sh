@@ -1,21 +1,23 @@
 #!/bin/bash
-# dev helper (gpurun, 1 GPU): bench line + reference arm + launch list + ncu captures + per-config probes of the final build
+# dev helper (gpurun, 1 GPU): what the driver runs at round end (GPU suite, smoke, bench, reference arm) + launch list +
+# ncu captures + per-config probes of the final build
 export MARQO_B200_USE_PREBUILT=1
 mkdir -p gpurun_out
+(time timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4) 2>&1 | tail -8
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
-tail -c 1500 gpurun_out/r02_bench_n1.err | tail -6
+tail -c 600 gpurun_out/r02_bench_n1.err | tail -3
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_ref.json 2>> gpurun_out/r02_bench_n1.err
 ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 700 --csv --log-file gpurun_out/r02_launches_final.csv \
     python bench.py --steps 3 --warmup 3 --quick --skip-topk --skip-cpu-baseline > /dev/null 2> gpurun_out/ncu_launch.err
 L14=open_clip/ViT-L-14/laion2b_s32b_b82k
-ncu --set full --clock-control none --import-source on -k regex:attention_os_kernel -s 3 -c 1 -o gpurun_out/r02_attn_os_final \
-    python tools/attn_probe.py 256 257 1024 16 0 6 > /dev/null 2> gpurun_out/ncu_attn.err
 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 101 -c 4 -o gpurun_out/r02_gemm_final \
     python tools/encoder_probe.py $L14 256 image 0 2 > /dev/null 2> gpurun_out/ncu_gemm.err
 for args in "hf/e5-base-v2 8 text 128 6" "hf/e5-base-v2 256 text 128 6" "open_clip/ViT-B-32/laion2b_s34b_b79k 256 image 0 6" \
             "open_clip/ViT-B-32/laion2b_s34b_b79k 256 text 77 6" "$L14 256 text 77 6" "hf/e5-large-v2 64 text 512 6" "$L14 256 image 0 8"; do
   python tools/encoder_probe.py $args 2>&1 | tail -2 | head -1
 done > gpurun_out/r02_probes.jsonl
-cat gpurun_out/r02_probes.jsonl | cut -c1-220
-python tools/attn_probe.py 2>&1 | tail -4
-cut -c1-1200 gpurun_out/r02_bench_n1.json
+cut -c1-200 gpurun_out/r02_probes.jsonl
+python bench.py --config cfg3 --docs 8192 --skip-cpu-baseline 2>/dev/null | cut -c1-700
+python bench.py --config cfg4 --chunks 16384 --skip-cpu-baseline 2>/dev/null | cut -c1-700
+cut -c1-400 gpurun_out/r02_bench_n1.json
