@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_tail,
                     const __nv_bfloat16* __restrict__ qkv,
                     __nv_bfloat16* __restrict__ out, int S, int W, int H, const int32_t* __restrict__ kv_len,
-                    float scale_log2e, int s_main, int has_tail, int total_units) {
+                    float scale_log2e, int s_main, int has_tail, int total_units, int reverse) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sQ = smem;                         // two 16 KB tiles
     uint8_t* sK = sQ + 2 * Q_BYTES;             // 256 keys x 64 dims, K-major 128B-swizzled (two TMA boxes)
@@ -248,7 +248,8 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         if (lane == 0) {
             uint32_t n = 0, uc = 0;
             for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++uc) {
-                const int b = u / H, h = u - b * H;
+                const int ur = reverse ? total_units - 1 - u : u;
+                const int b = ur / H, h = ur - b * H;
                 const int row_base = b * S;
                 for (int qb = 0; qb < q_blocks; ++qb, ++n) {
                     const uint32_t buf = n & 1;
@@ -293,7 +294,8 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         const size_t ld = (size_t)3 * W;
         const int gq = lane >> 2, tq = lane & 3;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++uc) {
-            const int b = u / H, h = u - b * H;
+            const int ur = reverse ? total_units - 1 - u : u;
+            const int b = ur / H, h = ur - b * H;
             const int row_base = b * S;
             int len = S;
             if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[b], 0));
@@ -301,7 +303,8 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
                 // (the remainder KEY is the tensor core's job: a 16-row K tile + a 16-column MMA per item, see the MMA warp)
                 const int nu = u + gridDim.x;
                 if (has_tail && lane == 0 && nu < total_units) {   // the next unit's remainder row: into L2 ahead of time
-                    const int nb = nu / H, nh = nu - nb * H;
+                    const int nur = reverse ? total_units - 1 - nu : nu;
+                    const int nb = nur / H, nh = nur - nb * H;
                     const __nv_bfloat16* nrow = qkv + ((size_t)nb * S + s_main) * ld + nh * HD;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(nrow + W));
@@ -456,7 +459,8 @@ attention_os_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_const
         const uint32_t lane_addr = tmem_base + (uint32_t(sp * 32) << 16);
         uint32_t n = 0;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-            const int b = u / H, h = u - b * H;
+            const int ur = reverse ? total_units - 1 - u : u;
+            const int b = ur / H, h = ur - b * H;
             const int row_base = b * S;
             int len = S;
             if (MASK == MASK_KEYLEN) len = min(S, max(kv_len[b], 0));
@@ -607,12 +611,15 @@ int launch_os(const __nv_bfloat16* qkv, __nv_bfloat16* out, int B, int S, int W,
     const int s_main = tail ? os::NK : S;
     const int total_units = B * H;
     const int grid = std::min(2 * sm_count(device), total_units);
+    // (batch, head) units are walked from the LAST sequence to the first: the QKV GEMM wrote the packed qkv matrix in
+    // ascending row order, so its last rows are the ones still in L2; MARQO_B200_ATTN_FORWARD=1 restores the forward order
+    static const int reverse = getenv("MARQO_B200_ATTN_FORWARD") == nullptr ? 1 : 0;
     if (mask == MASK_NONE)
         os::attention_os_kernel<MASK_NONE><<<grid, os::THREADS, os::SMEM_BYTES, stream>>>(
-            tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
+            tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units, reverse);
     else
         os::attention_os_kernel<MASK_KEYLEN><<<grid, os::THREADS, os::SMEM_BYTES, stream>>>(
-            tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units);
+            tmap, tmap_tail, qkv, out, S, W, H, kv_len, scale_log2e, s_main, tail ? 1 : 0, total_units, reverse);
     MB_CUDA(cudaGetLastError());
     return 1;
 }
