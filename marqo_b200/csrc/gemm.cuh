@@ -1,6 +1,6 @@
 // Persistent warp-specialised tcgen05 GEMM:  out[M,N] = epilogue( A[M,K] (bf16, K-major) x W[N,K]^T (bf16, K-major) )
 // CTA pairs (cta_group::2): one tcgen05.mma covers a 256 x BN tile across the two SMs of a cluster, each SM holding
-// 128 rows of A and BN/2 rows of W; fp32 accumulation in TMEM; TMA-fed 128B-swizzled smem ring (7 stages of 32 KB);
+// 128 rows of A and BN/2 rows of W; fp32 accumulation in TMEM; TMA-fed 128B-swizzled smem ring (5-6 stages of 32 KB);
 // double-buffered accumulators so the 8-warp epilogue of tile i overlaps the MMAs of tile i+1.
 #pragma once
 #include "common.cuh"
