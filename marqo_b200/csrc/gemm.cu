@@ -137,6 +137,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Explicit shared-space accesses for the epilogue's staging buffers: through generic pointers the compiler emitted generic
+// LD / ST plus 64-bit address arithmetic (the r02 profile of out_proj: 519 always-executed instructions per 32-column chunk, of
+// which 64 FADD, 24 loads and 17 stores were the work).
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void sts_u4(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
 // ---- fused LayerNorm (gemm.cuh: Epilogue::ln_*) ----
 // Chan et al.: merge (n_a, mean_a, M2_a) with (n_b, mean_b, M2_b)
 __device__ __forceinline__ void chan_merge(float& n_a, float& mean_a, float& m2_a, float n_b, float mean_b, float m2_b) {
@@ -454,7 +474,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const Epilogue& ep = p.ep;
         const float* const residual = GATHER ? nullptr : ep.residual;   // the patch-embed GEMM has no residual input
         uint8_t* stage_buf = smem_epi + (size_t)(warp - 2) * C::EPI_WARP_BYTES;
-        float* bias_row = reinterpret_cast<float*>(stage_buf + 32 * 128);
         uint8_t* res_buf = stage_buf + 32 * 128 + 128;        // residual block of the chunk about to be processed (cp.async)
         const int esz = ep.out_fp32 ? 4 : 2;                  // output element size
         const int cols_per_flush = 128 / esz;                 // 32 fp32 or 64 bf16 columns fill a 128-byte row
@@ -469,18 +488,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         // tile boundary: the next tile's first block is requested before this warp waits for that accumulator), in the
         // swizzled layout the lane == row read expects.  The r02 profile had out_proj (K = 1024: a tile every ~7 us) at
         // 44-47 % tensor pipe with its 8 epilogue warps taking one exposed L2 round trip per 32-column chunk.
+        // lane-constant shared addresses.  Coalesced phase (4 rows x 8 sixteen-byte units per instruction), row rr = 4 i + srow:
+        //   addr(i) = base + rr * 128 + ((sunit ^ (rr & 7)) << 4) = (co_even | co_odd picked by i & 1) + i * 512
+        // Row phase (lane == row): addr(j) = (base + lane * 128) | ((j ^ (lane & 7)) << 4) = rowp ^ (j << 4)
+        const uint32_t stage_s = ptx::smem_u32(stage_buf), res_s = ptx::smem_u32(res_buf);
+        const uint32_t co_even = (uint32_t)(srow * 128 + ((sunit ^ srow) << 4));
+        const uint32_t co_odd = co_even ^ 64u;
+        const uint32_t rowp = (uint32_t)(lane * 128 + ((lane & 7) << 4));
         int pref_t = -1, pref_c = -1;   // the (tile, chunk) whose residual block is in res_buf / on its way there
         auto prefetch_residual = [&](int tt, int cc) {
             if (GATHER || !residual || !has_cols || tt >= num_super) return;
             const int pm0 = ((tt / p.tiles_n) * CLUSTER + (int)crank) * BM + sp * 32;
             const int pn0 = (tt % p.tiles_n) * BN + half * HALF_COLS + cc * 32;
             if (pn0 >= p.N) return;
+            const float* src0 = residual + (size_t)(pm0 + srow) * ep.ldr + pn0 + sunit * 4;   // row slot 0 of this lane
+            const size_t step = (size_t)4 * ep.ldr;                                           // next row slot: 4 rows on
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int rr = i * 4 + srow;
-                const bool ok = pm0 + rr < p.M;
-                const float* src = ok ? residual + (size_t)(pm0 + rr) * ep.ldr + pn0 + sunit * 4 : residual;
-                const uint32_t dst = ptx::smem_u32(res_buf + rr * 128 + ((sunit ^ (rr & 7)) << 4));
+                const bool ok = pm0 + i * 4 + srow < p.M;
+                const float* src = ok ? src0 + i * step : residual;
+                const uint32_t dst = res_s + ((i & 1) ? co_odd : co_even) + i * 512;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
@@ -515,15 +542,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
+            // per tile: the 8 output rows this lane flushes (element offsets of their first column, validity mask)
+            uint32_t ooff[8];
+            uint32_t okmask = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int grow = wrow0 + i * 4 + srow;
+                long long orow = grow;
+                if (ep.remap_group > 0) {
+                    const int b = grow / ep.remap_group;
+                    orow = (long long)b * (ep.remap_group + 1) + 1 + (grow - b * ep.remap_group);
+                }
+                ooff[i] = (uint32_t)(orow * ep.ldo);
+                okmask |= (grow < p.M ? 1u : 0u) << i;
+            }
+            uint8_t* const out_base = reinterpret_cast<uint8_t*>(ep.out);
 #pragma unroll 1
             for (int c = 0; c < CHUNKS; ++c) {
                 const int n0 = nt0 + c * 32;
                 const bool cols_ok = has_cols && n0 < p.N;
-                // (1) start the long-latency global reads first: bias (one float per lane) and, for residual GEMMs,
-                //     the 32 x 32 fp32 residual block in coalesced order (4 rows x 128 B per instruction)
-                float bias_v = 0.f;
-                if (ep.bias && cols_ok) bias_v = __ldg(ep.bias + n0 + lane);
-                // (2) accumulator chunk: lane == row
+                // (1) accumulator chunk: lane == row
                 uint32_t v[32];
                 if (has_cols) {
                     ptx::tmem_ld_32x32b_x32(tmem_base + (uint32_t(sp * 32) << 16) + acc * BN + half * HALF_COLS + c * 32, v);
@@ -536,21 +574,27 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty[acc]), 0));
                 }
                 if (cols_ok) {
-                    bias_row[lane] = bias_v;
                     if (residual) {
                         // normally requested one chunk ago; a warp whose previous tile had no columns asks now
                         if (pref_t != t || pref_c != c) prefetch_residual(t, c);
                         asm volatile("cp.async.wait_group 0;" ::: "memory");
+                        __syncwarp();   // every lane's part of the residual block has landed
                     }
-                    __syncwarp();
                     float f[32];
+                    if (ep.bias) {
+                        // the chunk's 32 bias values: the same 128 bytes for every lane (L1 broadcast), no smem round trip
+                        const float4* b4 = reinterpret_cast<const float4*>(ep.bias + n0);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 b = *reinterpret_cast<const float4*>(bias_row + 4 * j);   // broadcast read
-                        f[4 * j] = __uint_as_float(v[4 * j]) + b.x;
-                        f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
-                        f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
-                        f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(b4 + j);
+                            f[4 * j] = __uint_as_float(v[4 * j]) + b.x;
+                            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + b.y;
+                            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + b.z;
+                            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                     }
                     if (ep.act == ACT_GELU) {
 #pragma unroll
@@ -575,7 +619,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     if (residual) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float4 b = *reinterpret_cast<const float4*>(res_buf + lane * 128 + ((j ^ (lane & 7)) << 4));
+                            const float4 b = lds_f4(res_s + (rowp ^ (uint32_t)(j << 4)));
                             f[4 * j] += b.x;
                             f[4 * j + 1] += b.y;
                             f[4 * j + 2] += b.z;
@@ -601,22 +645,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                             chan_merge(st_n, st_mean, st_m2, 32.f, cm, cq);
                         }
                     }
-                    // (3) own row -> staging buffer (swizzled 16-byte units)
+                    // (2) own row -> staging buffer (swizzled 16-byte units)
                     if (ep.out_fp32) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            *reinterpret_cast<float4*>(stage_buf + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-                                make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            sts_f4(stage_s + (rowp ^ (uint32_t)(j << 4)), f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                     } else {
                         const int ubase = (c % chunks_per_flush) * 4;   // this chunk fills units 0-3 or 4-7 of the row
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            *reinterpret_cast<uint4*>(stage_buf + lane * 128 + (((ubase + j) ^ (lane & 7)) << 4)) =
-                                make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                           pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+                            sts_u4(stage_s + (rowp ^ (uint32_t)((ubase + j) << 4)), pack_bf16x2(f[8 * j], f[8 * j + 1]),
+                                   pack_bf16x2(f[8 * j + 2], f[8 * j + 3]), pack_bf16x2(f[8 * j + 4], f[8 * j + 5]),
+                                   pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
                     }
                 }
-                // (4) flush full 128-byte rows: every instruction writes 4 rows x 128 contiguous bytes
+                // (3) flush full 128-byte rows: every instruction writes 4 rows x 128 contiguous bytes
                 const bool flush = (c % chunks_per_flush) == chunks_per_flush - 1 || c == CHUNKS - 1;
                 if (flush && has_cols) {
                     __syncwarp();
@@ -626,17 +669,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     if (col < p.N && sunit < filled_units) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const int rr = i * 4 + srow;
-                            const int grow = wrow0 + rr;
-                            if (grow < p.M) {
-                                long long orow = grow;
-                                if (ep.remap_group > 0) {
-                                    const int b = grow / ep.remap_group;
-                                    orow = (long long)b * (ep.remap_group + 1) + 1 + (grow - b * ep.remap_group);
-                                }
-                                const uint4 val = *reinterpret_cast<const uint4*>(stage_buf + rr * 128 + ((sunit ^ (rr & 7)) << 4));
-                                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(ep.out) +
-                                                          ((size_t)orow * ep.ldo + col) * esz) = val;
+                            if ((okmask >> i) & 1u) {
+                                const uint4 val = lds_u4(stage_s + ((i & 1) ? co_odd : co_even) + i * 512);
+                                *reinterpret_cast<uint4*>(out_base + (size_t)(ooff[i] + (uint32_t)col) * esz) = val;
                             }
                         }
                     }
@@ -859,6 +894,10 @@ void launch(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, int M, int 
     if (K <= 0 || K % BK != 0) fail(B200_ERR_INTERNAL, "gemm: K = %d must be a positive multiple of %d", K, BK);
     if (N % 32 != 0) fail(B200_ERR_INTERNAL, "gemm: N = %d must be a multiple of 32", N);
     if (lda % 8 != 0 || ep.ldo % 8 != 0) fail(B200_ERR_INTERNAL, "gemm: leading dimensions must be multiples of 8");
+    {   // the epilogues address the output with 32-bit element offsets
+        const long long out_rows = (long long)M + (ep.remap_group > 0 ? M / ep.remap_group + 1 : 0) + 256;
+        if (out_rows * ep.ldo >= (1LL << 32)) fail(B200_ERR_UNSUPPORTED, "gemm: output of %lld x %d elements is too large", out_rows, ep.ldo);
+    }
     if (ep.ln_gamma != nullptr) {
         if (!ep.out_fp32 || ep.ldo != N || N % 128 != 0 || N > 1024 || ep.remap_group != 0 || !ep.ln_beta ||
             !ep.ln_counters || !ep.ln_stats || (!ep.ln_out_bf16 && !ep.ln_out_f32))
