@@ -45,8 +45,10 @@ struct Cfg {
     // (EW = 16 keeps the bias row inside the transpose buffer, so the smem ring stays 6 stages deep at BN = 256)
     // (+ for the general epilogue of a GEMM that can have a residual input: a second 32 x 128 B buffer the NEXT chunk's
     //  residual block is prefetched into with cp.async while the current chunk is processed)
+    // Both buffers are 4 KB and 1024-byte aligned: TMA's hardware 128B swizzle (residual in, fp32 result out) works on
+    // absolute shared-memory address bits, and must coincide with the epilogue's own (16-byte unit ^ (row & 7)) pattern.
     static constexpr uint32_t RES_BYTES = (EW == 8 && !GATHER) ? 32 * 128 : 0;
-    static constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_ROW_BYTES + (EW == 16 ? 0 : 128) + RES_BYTES;
+    static constexpr uint32_t EPI_WARP_BYTES = 32 * EPI_ROW_BYTES + ((EW == 16 || !GATHER) ? 0 : 128) + RES_BYTES;
     static constexpr uint32_t EPI_BYTES = EW * EPI_WARP_BYTES;
     static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - (int)EPI_BYTES - (int)RAW_BYTES) / (int)STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -66,6 +68,7 @@ struct Params {
     int tiles_m, tiles_n;   // tiles_m counts 128-row blocks
     int super_m;            // ceil(tiles_m / CLUSTER)
     Epilogue ep;
+    int tma_io;             // fp32 output / residual blocks through TMA (tmap_o / tmap_r are valid)
     // GATHER only: uint8 HWC images [n, S, S, 3]; A row r = patch r (image r / (g*g), then row-major in the grid)
     const uint8_t* img;
     int g;                  // patches per image side
@@ -254,7 +257,8 @@ __device__ __forceinline__ void ln_apply_subtile(const Epilogue& ep, int M, int 
 
 template <int BN, int EW, bool GATHER>
 __global__ void __launch_bounds__(64 + 32 * EW + (GATHER ? 32 * GATHER_WARPS : 0), 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, Params p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_r, Params p) {
     using C = Cfg<BN, EW, GATHER>;
     constexpr int EPI_WARPS = EW;
     extern __shared__ uint8_t smem_raw[];
@@ -267,7 +271,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;
     uint64_t* tempty = tfull + ACC_STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + ACC_STAGES);
+    uint64_t* res_full = tempty + ACC_STAGES;   // [8] one per epilogue warp: its residual block has landed (TMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 8);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -285,6 +290,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             ptx::mbar_init(&full[i], CLUSTER + (GATHER ? CLUSTER * GATHER_WARPS : 0));
             ptx::mbar_init(&empty[i], 1);         // one multicast tcgen05.commit per use, in each CTA
         }
+        for (int i = 0; i < 8; ++i) ptx::mbar_init(&res_full[i], 1);
         for (int i = 0; i < ACC_STAGES; ++i) {
             ptx::mbar_init(&tfull[i], 1);
             ptx::mbar_init(&tempty[i], CLUSTER * EPI_WARPS);   // leader's copy: epilogue warps of both CTAs
@@ -474,7 +480,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const Epilogue& ep = p.ep;
         const float* const residual = GATHER ? nullptr : ep.residual;   // the patch-embed GEMM has no residual input
         uint8_t* stage_buf = smem_epi + (size_t)(warp - 2) * C::EPI_WARP_BYTES;
-        uint8_t* res_buf = stage_buf + 32 * 128 + 128;        // residual block of the chunk about to be processed (cp.async)
+        uint8_t* res_buf = stage_buf + 32 * 128 + (GATHER ? 128 : 0);   // residual block of the chunk about to be processed
+        // fp32 results without token remap leave through TMA (one bulk tensor store per 32 x 32 block instead of 8 shared
+        // loads + 8 global stores + their address arithmetic per lane), residual blocks arrive through TMA: p.tma_io.
+        // (Not with the fused LayerNorm: its strip counters must not run ahead of asynchronous stores.)
+        const bool tma_io = !GATHER && p.tma_io != 0 && ep.ln_gamma == nullptr;
+        uint64_t* my_res_full = &res_full[warp - 2];
+        uint32_t res_phase = 0;
         const int esz = ep.out_fp32 ? 4 : 2;                  // output element size
         const int cols_per_flush = 128 / esz;                 // 32 fp32 or 64 bf16 columns fill a 128-byte row
         // bf16 results are staged two chunks (64 columns) per flush; a residual block occupies the whole buffer, so
@@ -501,6 +513,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             const int pm0 = ((tt / p.tiles_n) * CLUSTER + (int)crank) * BM + sp * 32;
             const int pn0 = (tt % p.tiles_n) * BN + half * HALF_COLS + cc * 32;
             if (pn0 >= p.N) return;
+            if (tma_io) {
+                if (lane == 0) {
+                    ptx::mbar_arrive_expect_tx(my_res_full, 32 * 128);
+                    ptx::tma_load_2d(res_buf, &tmap_r, my_res_full, pn0, pm0, ptx::kEvictNormal);   // rows >= M: zero fill
+                }
+                pref_t = tt;
+                pref_c = cc;
+                return;
+            }
             const float* src0 = residual + (size_t)(pm0 + srow) * ep.ldr + pn0 + sunit * 4;   // row slot 0 of this lane
             const size_t step = (size_t)4 * ep.ldr;                                           // next row slot: 4 rows on
 #pragma unroll
@@ -577,8 +598,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                     if (residual) {
                         // normally requested one chunk ago; a warp whose previous tile had no columns asks now
                         if (pref_t != t || pref_c != c) prefetch_residual(t, c);
-                        asm volatile("cp.async.wait_group 0;" ::: "memory");
-                        __syncwarp();   // every lane's part of the residual block has landed
+                        if (tma_io) {
+                            ptx::mbar_wait(my_res_full, res_phase);
+                            res_phase ^= 1;
+                        } else {
+                            asm volatile("cp.async.wait_group 0;" ::: "memory");
+                            __syncwarp();   // every lane's part of the residual block has landed
+                        }
                     }
                     float f[32];
                     if (ep.bias) {
@@ -646,6 +672,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         }
                     }
                     // (2) own row -> staging buffer (swizzled 16-byte units)
+                    if (tma_io) {   // the previous block's bulk store must have read the buffer out
+                        if (lane == 0) ptx::tma_store_wait_read<0>();
+                        __syncwarp();
+                    }
                     if (ep.out_fp32) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -661,7 +691,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                 }
                 // (3) flush full 128-byte rows: every instruction writes 4 rows x 128 contiguous bytes
                 const bool flush = (c % chunks_per_flush) == chunks_per_flush - 1 || c == CHUNKS - 1;
-                if (flush && has_cols) {
+                if (tma_io) {
+                    if (cols_ok && wrow0 < p.M) {
+                        ptx::fence_proxy_async_smem();   // generic-proxy staging stores -> visible to the bulk store
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_2d(&tmap_o, stage_buf, n0, wrow0);   // rows >= M / columns >= N are clipped
+                            ptx::tma_store_commit();
+                        }
+                    }
+                } else if (flush && has_cols) {
                     __syncwarp();
                     const int fc0 = nt0 + (c / chunks_per_flush) * chunks_per_flush * 32;   // first column held in the buffer
                     const int col = fc0 + sunit * (16 / esz);
@@ -705,6 +744,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             }
         }
         if (!GATHER && ln_on && pend_row0 >= 0) ln_apply_subtile<CHUNKS>(ep, p.M, p.N, pend_row0, pend_col0, ln_parts, lane);
+        if (tma_io && lane == 0) ptx::tma_store_wait<0>();
     } else if (GATHER && warp >= 2 + EW) {
         // ---------------------------------------------------------------- patch gather (uint8 HWC -> bf16 A stage)
         // Warp gw owns rows gw*32 .. gw*32+31 of this CTA's 128-row A tile: lane == patch.  Per patch pixel row dy the
@@ -861,7 +901,21 @@ static void launch_bn(const __nv_bfloat16* A, int lda, const __nv_bfloat16* W, i
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    MB_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EW, GATHER>, ta, tb, p));
+    // fp32 output without token remap: the epilogue's 32 x 32 blocks (128-byte rows, 128B swizzle) go through TMA
+    static const bool no_tma_io = getenv("MARQO_B200_GEMM_NO_TMA_EPILOGUE") != nullptr;   // A/B timing switch
+    p.tma_io = (!GATHER && EW == 8 && !no_tma_io && ep.out_fp32 && ep.remap_group == 0 && ep.rowbias == nullptr &&
+                ep.ldo % 4 == 0 && (ep.residual == nullptr || ep.ldr % 4 == 0) &&
+                (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0)
+                   ? 1 : 0;
+    CUtensorMap to = tb, tr = tb;
+    if (p.tma_io) {
+        to = make_tmap_2d(ep.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N, (uint64_t)M, (uint64_t)ep.ldo * 4, 32, 32,
+                          CU_TENSOR_MAP_SWIZZLE_128B);
+        if (ep.residual)
+            tr = make_tmap_2d(ep.residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (uint64_t)N, (uint64_t)M,
+                              (uint64_t)ep.ldr * 4, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+    MB_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, EW, GATHER>, ta, tb, to, tr, p));
 }
 
 bool patch_gather_supported(int S, int patch) {

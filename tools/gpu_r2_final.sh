@@ -1,6 +1,6 @@
 #!/bin/bash
 # dev helper (gpurun, 1 GPU): what the driver runs at round end (GPU suite, smoke, bench, reference arm) + launch list +
-# ncu captures + per-config probes of the final build
+# ncu captures of the final build
 export MARQO_B200_USE_PREBUILT=1
 mkdir -p gpurun_out
 (time timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -4) 2>&1 | tail -8
@@ -13,11 +13,4 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 700 --csv --
 L14=open_clip/ViT-L-14/laion2b_s32b_b82k
 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 101 -c 4 -o gpurun_out/r02_gemm_final \
     python tools/encoder_probe.py $L14 256 image 0 2 > /dev/null 2> gpurun_out/ncu_gemm.err
-for args in "hf/e5-base-v2 8 text 128 6" "hf/e5-base-v2 256 text 128 6" "open_clip/ViT-B-32/laion2b_s34b_b79k 256 image 0 6" \
-            "open_clip/ViT-B-32/laion2b_s34b_b79k 256 text 77 6" "$L14 256 text 77 6" "hf/e5-large-v2 64 text 512 6" "$L14 256 image 0 8"; do
-  python tools/encoder_probe.py $args 2>&1 | tail -2 | head -1
-done > gpurun_out/r02_probes.jsonl
-cut -c1-200 gpurun_out/r02_probes.jsonl
-python bench.py --config cfg3 --docs 8192 --skip-cpu-baseline 2>/dev/null | cut -c1-700
-python bench.py --config cfg4 --chunks 16384 --skip-cpu-baseline 2>/dev/null | cut -c1-700
 cut -c1-400 gpurun_out/r02_bench_n1.json
