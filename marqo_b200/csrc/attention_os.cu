@@ -6,7 +6,9 @@
 //   same softmax, see the softmax warps), written back INTO TMEM as packed bf16 pairs over the columns of S the pass has
 //   already consumed ([0, 128)),
 //   O = P V          (M = 128, N = 64, K = 256; A operand read from TMEM, V MN-major from smem) -> columns [128, 192)
-//   epilogue: O / l (+ the remainder key of 257 = 256 + 1) -> bf16.
+//   the 257th token's key (257 = 256 + 1): its K / V rows arrive as 16-row TMA boxes, its scores against the item's 128 rows
+//   are a 16-column MMA issued together with P V into columns S no longer needs ([192, 208)),
+//   epilogue: O / l with the remainder key folded in (exact online update) -> bf16.
 // Compared with attention_tc.cu (128-key blocks, P through shared memory, running maximum + O rescale) an item has one
 // S / P / O hand-off instead of two of each, no P stores to shared memory, no fence.proxy.async, no rescale branch, and
 // K / V are loaded ONCE per (batch, head) and shared by its two query blocks (Q is double buffered).
@@ -17,8 +19,8 @@
 //   warp 0  TMA producer: Q tiles (2-deep ring), K and V (256 rows each, one load per (batch, head))
 //   warp 1  tcgen05.mma issuer
 //   warps 2-5  softmax / epilogue, one thread per query row (TMEM lane == row)
-//   warp 6  remainder key (scores against the 128 rows from the Q tile in smem + its V row, staged for the epilogue)
-//           and remainder query row (mma.sync against the K / V tiles while they sit in shared memory)
+//   warp 6  the remainder QUERY row (mma.sync against the K / V tiles while they sit in shared memory), once per
+//           (batch, head), as soon as the tiles have landed
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
